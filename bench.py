@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- photons/ms of the photon random-walk hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload sphshells|cube60|...]
+
+One "step" = one pass of the hot path over one batch of synthetic input: `--photons` photons (default 1e7, the
+BASELINE config C2 count) launched from the device-resident session.  `value` is device-timed (CUDA events, max over
+ranks) with every input already in HBM; `e2e` is the same metric through the public one-call API with HOST buffers
+(mesh upload, kernel, result download and normalisation inside the timed region).  N>1: one process per GPU under
+torchrun, photons shard (weak scaling: every rank simulates `--photons`), the fluence volume is sum-reduced to rank 0
+inside every timed step.
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/mmc_ref when it was built, else the
+oracle port) on the same workload, on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_STEP = {"elem": 92, "grid": 92}        # 84 B gathered + one fp32 atomic payload (RMW)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# workloads (BASELINE.json configs)
+# --------------------------------------------------------------------------------------------------------------------
+def workload(name, method=None):
+    from mmc_b200 import meshgen
+    gold = os.path.join(ROOT, "tests", "golden")
+    if name == "sphshells":          # configs[1]: shipped dmmc_sphshells mesh + json (reflection on, 10 gates)
+        z = np.load(os.path.join(gold, "sphshells_mesh.npz"))
+        cfg = dict(node=z["node"], elem=z["elem"], elemprop=z["etype"], prop=np.vstack([[0, 0, 1, 1], z["prop"]]), evol=z["evol"],
+                   srcpos=(30.0, 30.1, 0.0), srcdir=(0, 0, 1), e0=4916, tstart=0.0, tend=5e-9, tstep=5e-10,
+                   isreflect=1, seed=1648335518, method=method or "grid", steps=(1.0, 1.0, 1.0), basisorder=0)
+        desc = "examples/sphshells dmmc_sphshells mesh (3723 nodes/21256 tets, 4 media, n-mismatch, reflection on), pencil, 10 gates, RayTracer=%s" % cfg["method"]
+    elif name == "cube60":           # configs[0]
+        node, elem, et = meshgen.cube60()
+        cfg = dict(node=node, elem=elem, elemprop=et, prop=[[0, 0, 1, 1], [0.005, 1.0, 0.01, 1.37]],
+                   srcpos=(30.1, 30.2, 0.0), srcdir=(0, 0, 1), e0=4497, tstart=0.0, tend=5e-9, tstep=1e-10,
+                   isreflect=0, seed=1648335518, method=method or "elem", basisorder=0)
+        desc = "examples/validation cube60 (29791 nodes/135000 tets), mua=0.005 mus=1 g=0.01 n=1.37, pencil, 50 gates, RayTracer=%s" % cfg["method"]
+    elif name == "skinvessel":       # configs[2]
+        z = np.load(os.path.join(gold, "skinvessel_mesh.npz"))
+        cfg = dict(node=z["node"], elem=z["elem"], elemprop=z["etype"], prop=np.vstack([[0, 0, 1, 1], z["prop"]]), evol=z["evol"],
+                   srcpos=(0.5, 0.5, -0.005), srcdir=(0, 0, 1), srctype="disk", srcparam1=(0.3, 0, 0, 0), e0=6178,
+                   tstart=0.0, tend=5e-8, tstep=5e-9, isreflect=0, seed=1648335518, method=method or "grid",
+                   steps=(0.005, 0.005, 0.005), basisorder=0)
+        desc = "examples/skinvessel dmmc mesh (1142 nodes/6394 tets), disk source, 10 gates, 200^3 dual grid"
+    elif name == "headlike":         # configs[3] stand-in (colin27 is not shipped)
+        node, elem, et = meshgen.head_like()
+        prop = [[0, 0, 1, 1], [0.019, 7.8, 0.89, 1.37], [0.019, 7.8, 0.89, 1.37], [0.004, 0.009, 0.89, 1.37],
+                [0.02, 9.0, 0.89, 1.37], [0.08, 40.9, 0.84, 1.37]]
+        cfg = dict(node=node, elem=elem, elemprop=et, prop=prop, srcpos=(42.0, 52.0, 91.0), srcdir=(0, 0, -1),
+                   tstart=0.0, tend=5e-9, tstep=5e-10, isreflect=1, seed=1648335518, method=method or "elem", basisorder=0,
+                   issavedet=1, detpos=[(52.0, 52.0, 90.0, 3.0)], maxdetphoton=3000000)
+        desc = "synthetic colin27-scale head (5 tissue ellipsoids on a T5 lattice), detectors + partial paths"
+    else:
+        raise SystemExit("unknown workload " + name)
+    return cfg, desc
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# the reference arm / CPU baseline
+# --------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(cfg, nphoton, threads):
+    """One bounded sample of the workload through the reference's own CPU implementation; returns photons/ms."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    from mmc_b200 import api
+    node, elem = np.asarray(cfg["node"], np.float32), np.asarray(cfg["elem"], np.int32)
+    et, med = np.asarray(cfg["elemprop"], np.int32), np.asarray(cfg["prop"], np.float32)[1:]
+    st = cfg.get("srctype", 0)
+    kw = dict(nphoton=int(nphoton), seed=cfg["seed"], srcpos=cfg["srcpos"], srcdir=cfg["srcdir"],
+              srctype=api.SRCTYPES.index(st) if isinstance(st, str) else st,
+              srcparam1=cfg.get("srcparam1", (0, 0, 0, 0)), srcparam2=cfg.get("srcparam2", (0, 0, 0, 0)),
+              tstart=cfg["tstart"], tend=cfg["tend"], tstep=cfg["tstep"], e0=cfg.get("e0", 0), isreflect=cfg["isreflect"],
+              method=api.METHODS[cfg["method"]], basisorder=cfg.get("basisorder", 0), steps=cfg.get("steps", (1.0,))[0],
+              issavedet=cfg.get("issavedet", 0), detpos=cfg.get("detpos"), evol=cfg.get("evol"))
+    if orc.ref_available():
+        t0 = time.time()
+        r = orc.run_ref(node, elem, et, med, nthread=threads, **kw)
+        wall = (time.time() - t0) * 1e3
+        return dict(value=r.get("speed", nphoton / wall), kind="reference", wall_ms=wall, raytet=r.get("raytet"))
+    t0 = time.time()
+    o = orc.run(node, elem, et, med, nthread=threads, **kw)
+    wall = (time.time() - t0) * 1e3
+    return dict(value=nphoton / wall, kind="port", wall_ms=wall, raytet=o["raytet"])
+
+
+def reference_arm(args, cfg, desc):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = int(args.ref_photons)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_run(cfg, sample, threads)
+        if i >= args.warmup:
+            vals.append(r)
+    wall = sum(v["wall_ms"] for v in vals)
+    value = float(np.mean([v["value"] for v in vals]))
+    line = {"impl": "reference", "metric": "photons/ms", "value": value, "unit": "photons/ms", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / max(1, len(vals)), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "photons_per_step": sample},
+            "cpu_baseline": {"value": value, "unit": "photons/ms", "cores": threads, "kind": vals[0]["kind"],
+                             "sample": "%d photons per step of the same workload, reference CPU (SSE4 BLB tracer, OpenMP, all host threads)" % sample},
+            "e2e": {"value": value, "unit": "photons/ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="sphshells")
+    ap.add_argument("--method", default=None)
+    ap.add_argument("--photons", type=float, default=1e7)
+    ap.add_argument("--ref-photons", type=float, default=2e5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    cfg, desc = workload(args.workload, args.method)
+    nphoton = int(args.photons)
+    cfg["nphoton"] = nphoton
+
+    if args.impl == "reference":
+        reference_arm(args, cfg, desc)
+        return
+
+    import torch
+    import mmc_b200
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg["gpuid"] = local + 1
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    sess = mmc_b200.Session(cfg)
+    dp = sess.devptrs()
+    # the accumulator volume lives in a torch tensor so that NCCL can reduce it in place
+    field = torch.zeros(dp.fieldlen, dtype=torch.float64 if dp.field_is_double else torch.float32, device=dev)
+    sess.set_field_buffer(field.data_ptr())
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(i):
+        flush.fill_(i & 0xFF)                      # evict the mesh and the volume from L2 between timed steps
+        torch.cuda.synchronize()
+        sess.launch(nphoton, photon_offset=0, seed=cfg["seed"], seed_offset=rank + world * i)
+        ms = sess.sync()
+        if dist is not None:
+            dist.reduce(field, dst=0, op=dist.ReduceOp.SUM)
+        return ms
+
+    for i in range(args.warmup):
+        step(i)
+    sess.reset()
+    field.zero_()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    kern_ms, step_ms = [], []
+    for i in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.fill_(i & 0xFF)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        sess.launch(nphoton, photon_offset=0, seed=cfg["seed"], seed_offset=rank + world * (args.warmup + i), stream=torch.cuda.current_stream().cuda_stream)
+        if dist is not None:
+            dist.reduce(field, dst=0, op=dist.ReduceOp.SUM)
+        e1.record()
+        torch.cuda.synchronize()
+        kern_ms.append(sess.sync())
+        step_ms.append(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, total_kern_ms = float(t[0]), float(t[1])
+    res = sess.fetch()
+    raytet = res["raytet"]
+    absorbed = float(res["energyabs"][0] / max(res["energytot"][0], 1e-30))
+    sess.close()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    value = world * nphoton * args.steps / total_ms
+    hbm, peak_src = peaks()
+    bps = BYTES_PER_STEP.get(cfg["method"], 92)
+    steps_per_launch = raytet / args.steps
+    kernel_ms = total_kern_ms / args.steps
+    achieved = steps_per_launch * bps / (kernel_ms * 1e-3) / 1e9
+    line = {"metric": "photons/ms", "value": value, "unit": "photons/ms", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "photons_per_step_per_gpu": nphoton, "l2": "flushed between timed steps (192 MiB fill)",
+                       "accumulator": "f64 red.global.add" if dp.field_is_double else "f32 red.global.add",
+                       "raytet_steps_per_photon": steps_per_launch / nphoton, "absorbed_fraction": absorbed},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms,
+                         "note": "algorithmic bytes = %d B per ray-tet step x %.3g steps per launch; tables are L2-resident so HBM is the outer bound, see profiles/ for the L2-gather and atomic micro-benchmarks" % (bps, steps_per_launch)}}
+
+    if not args.no_e2e:
+        # end to end through the public one-call API: host arrays in, host arrays out (mesh prep, H2D, kernel, D2H, normalise)
+        t0 = time.perf_counter()
+        r = mmc_b200.run(dict(cfg, gpuid=1))
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        ne, nn = len(cfg["elem"]), len(cfg["node"])
+        h2d = ne * (96 + 16 + 16) + nn * 12 + 4 * 4 * 1024 * 148 * 9
+        line["e2e"] = {"value": nphoton / e2e_ms, "unit": "photons/ms", "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(r["raw"].size * 8), "ms": e2e_ms, "kernel_ms": float(r["kernel_ms"])}
+
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        c = cpu_reference_run(cfg, int(args.ref_photons), threads)
+        line["cpu_baseline"] = {"value": c["value"], "unit": "photons/ms", "cores": threads, "kind": c["kind"],
+                                "sample": "%d photons of the same workload, one run, reference CPU path with all host threads" % int(args.ref_photons)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,46 @@
+"""Builds libmmc_b200.so (the C-ABI library: CUDA kernels for sm_100a + host layer) in-tree with nvcc.
+
+    python -m mmc_b200.build            # build if stale
+    python -m mmc_b200.build --force
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libmmc_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+SOURCES = ["mmcb_kernel.cu", "mmcb_host.cu"]
+HEADERS = ["mmcb_types.h", os.path.join("..", "..", "include", "mmc_b200.h")]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-use_fast_math", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--cudart", "static"]
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False, extra=()):
+    if not force and not stale():
+        return LIB
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        cmd = [NVCC] + FLAGS + list(extra) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+        objs.append(obj)
+    subprocess.check_call([NVCC, "-shared", "--cudart", "static", "-o", LIB] + objs)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

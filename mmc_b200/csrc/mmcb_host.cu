@@ -1,0 +1,1528 @@
+// mmc_b200 host layer: the C-ABI of include/mmc_b200.h.
+//
+// Replaces the reference's per-device CUDA driver (src/mmc_cu_host.cu:204-1528 mmc_run_simulation) and the host-side
+// precompute its callers run in mmc_prep (src/mmc_host.c:136-165): volumes, face neighbours, BLB face planes,
+// initial-element search, exterior-face numbering, surface nodal-volume correction, normalisation.
+// The tables are repacked into the structure-of-records layout of mmcb_types.h before upload.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mmc_b200.h"
+#include "mmcb_types.h"
+
+// kernel-side launchers (mmcb_kernel.cu)
+extern "C" int mmcb_k_upload_param(const mmcb_kparam* hp, const float* det4, int detnum, cudaStream_t st);
+extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int isgrid, int isdet, int isgeneral, cudaStream_t st);
+extern "C" int mmcb_k_occupancy(int block, size_t smem, int isgrid, int isdet, int isgeneral, int* blocks_per_sm);
+extern "C" int mmcb_k_spread_nodes(const void* efield, double* nfield, const int* elem, int ne, int nn, int maxgate, int srcnum, cudaStream_t st);
+extern "C" int mmcb_k_acc_to_double(const void* in, double* out, size_t n, cudaStream_t st);
+extern "C" int mmcb_k_acc_is_double(void);
+extern "C" int mmcb_k_rng(const uint32_t* dseeds, int nstream, int ndraw, float* dout, unsigned long long* dstate, cudaStream_t st);
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int g_code = 0;
+
+int fail(int code, const char* fmt, ...) {
+    g_code = code;
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(MMCB_ERR_CUDA, "CUDA error %d (%s) at %s:%d", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define CUK(call) do { int e_ = (call); if (e_ != 0) return fail(MMCB_ERR_CUDA, "CUDA error %d (%s) at %s:%d", e_, cudaGetErrorString((cudaError_t)e_), __FILE__, __LINE__); } while (0)
+
+const float EPSF = 1e-6f;
+const float VERY_BIG = 1e30f;
+// index tables, src/mmc_mesh.c:59-103 and src/mmc_highorder.cpp:50
+const int OUT[4][3] = {{0, 3, 1}, {3, 2, 1}, {0, 2, 3}, {0, 1, 2}};
+const int FACEMAP[4] = {2, 0, 1, 3};
+const int FACEORDER[4] = {1, 3, 2, 0};
+const int IFACEORDER[4] = {3, 0, 2, 1};
+const int FACELIST[4][3] = {{0, 1, 2}, {0, 1, 3}, {0, 2, 3}, {1, 2, 3}};
+
+inline const float* nd(const float* node, int id1) {
+    return node + 3 * (size_t)(id1 - 1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// glibc rand() (TYPE_3 additive feedback generator) restated so that seeds do not depend on libc state
+// ---------------------------------------------------------------------------------------------------
+struct GlibcRand {
+    int32_t r[34];
+    uint32_t ring[31];
+    int pos;
+    explicit GlibcRand(unsigned int seed) {
+        if (seed == 0) {
+            seed = 1;
+        }
+
+        std::vector<uint32_t> v(344);
+        int32_t word = (int32_t)seed;
+        v[0] = (uint32_t)word;
+
+        for (int i = 1; i < 31; i++) {
+            long hi = word / 127773, lo = word % 127773;
+            word = (int32_t)(16807 * lo - 2836 * hi);
+
+            if (word < 0) {
+                word += 2147483647;
+            }
+
+            v[i] = (uint32_t)word;
+        }
+
+        for (int i = 31; i < 34; i++) {
+            v[i] = v[i - 31];
+        }
+
+        for (int i = 34; i < 344; i++) {
+            v[i] = v[i - 31] + v[i - 3];
+        }
+
+        for (int i = 0; i < 31; i++) {
+            ring[i] = v[344 - 31 + i];
+        }
+
+        pos = 0;
+    }
+    uint32_t next() {
+        // o_k = o_{k-31} + o_{k-3}
+        uint32_t val = ring[pos] + ring[(pos + 28) % 31];
+        ring[pos] = val;
+        pos = (pos + 1) % 31;
+        return val >> 1;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// prepared mesh (host side)
+// ---------------------------------------------------------------------------------------------------
+struct PrepMesh {
+    int nn = 0, ne = 0, nf = 0, prop = 0, isextdet = 0, e0_from_src = 0;
+    std::vector<float> node;
+    std::vector<int> elem, type, facenb, srcelem, detelem;
+    std::vector<mmcb_medium> med;
+    std::vector<float> evol, nvol;
+    float nmin[3], nmax[3];
+};
+
+void volumes(int nn, const float* node, int ne, int* elem, const int* type, float* evol, float* nvol) {
+    // mesh_getvolume, src/mmc_mesh.c:910-948
+    std::fill(nvol, nvol + nn, 0.f);
+
+    for (int i = 0; i < ne; i++) {
+        int* ee = elem + 4 * (size_t)i;
+        const float* n0 = nd(node, ee[0]), *n1 = nd(node, ee[1]), *n2 = nd(node, ee[2]), *n3 = nd(node, ee[3]);
+        float dx = n2[0] - n3[0], dy = n2[1] - n3[1], dz = n2[2] - n3[2];
+        float v = n1[0] * (n2[1] * n3[2] - n2[2] * n3[1]) - n1[1] * (n2[0] * n3[2] - n2[2] * n3[0]) + n1[2] * (n2[0] * n3[1] - n2[1] * n3[0]);
+        v += -n0[0] * ((n2[1] * n3[2] - n2[2] * n3[1]) + n1[1] * dz - n1[2] * dy);
+        v += +n0[1] * ((n2[0] * n3[2] - n2[2] * n3[0]) + n1[0] * dz - n1[2] * dx);
+        v += -n0[2] * ((n2[0] * n3[1] - n2[1] * n3[0]) + n1[0] * dy - n1[1] * dx);
+        v = -v;
+
+        if (v < 0.f) {
+            std::swap(ee[2], ee[3]);
+            v = -v;
+        }
+
+        v *= (1.f / 6.f);
+        evol[i] = v;
+
+        if (type && type[i] == 0) {
+            continue;
+        }
+
+        for (int j = 0; j < 4; j++) {
+            nvol[ee[j] - 1] += v * 0.25f;
+        }
+    }
+}
+
+void facenb_build(int ne, const int* elem, int* facenb) {
+    // mesh_getfacenb, src/mmc_highorder.cpp:124-159: match faces through their sorted node triples
+    struct Key {
+        int a, b, c, slot;
+    };
+    std::vector<Key> k((size_t)ne * 4);
+
+    for (int i = 0; i < ne; i++) {
+        const int* ee = elem + 4 * (size_t)i;
+
+        for (int j = 0; j < 4; j++) {
+            int v[3] = {ee[FACELIST[j][0]], ee[FACELIST[j][1]], ee[FACELIST[j][2]]};
+            std::sort(v, v + 3);
+            k[(size_t)i * 4 + j] = {v[0], v[1], v[2], i * 4 + j};
+        }
+    }
+
+    std::sort(k.begin(), k.end(), [](const Key & x, const Key & y) {
+        if (x.a != y.a) {
+            return x.a < y.a;
+        }
+
+        if (x.b != y.b) {
+            return x.b < y.b;
+        }
+
+        if (x.c != y.c) {
+            return x.c < y.c;
+        }
+
+        return x.slot < y.slot;
+    });
+    std::fill(facenb, facenb + (size_t)ne * 4, 0);
+
+    for (size_t i = 0; i + 1 < k.size(); i++) {
+        if (k[i].a == k[i + 1].a && k[i].b == k[i + 1].b && k[i].c == k[i + 1].c) {
+            facenb[k[i].slot] = (k[i + 1].slot >> 2) + 1;
+            facenb[k[i + 1].slot] = (k[i].slot >> 2) + 1;
+            i++;
+        }
+    }
+}
+
+int barycentric(const float* node, const int* elem, int ne, int e0, float* bary, const float* srcpos) {
+    // mesh_barycentric, src/mmc_mesh.c:1170-1206
+    if (e0 < 1 || e0 > ne) {
+        return 1;
+    }
+
+    const int* ee = elem + 4 * (size_t)(e0 - 1);
+    float s = 0.f;
+
+    for (int i = 0; i < 4; i++) {
+        const float* a = nd(node, ee[OUT[i][0]]), *b = nd(node, ee[OUT[i][1]]), *c = nd(node, ee[OUT[i][2]]);
+        float AB[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, AC[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+        float S[3] = {srcpos[0] - a[0], srcpos[1] - a[1], srcpos[2] - a[2]};
+        float N[3] = {AB[1]* AC[2] - AB[2]* AC[1], AB[2]* AC[0] - AB[0]* AC[2], AB[0]* AC[1] - AB[1]* AC[0]};
+        bary[FACEMAP[i]] = -(S[0] * N[0] + S[1] * N[1] + S[2] * N[2]);
+    }
+
+    for (int i = 0; i < 4; i++) {
+        if (bary[i] < 0.f) {
+            return 1;
+        }
+
+        s += bary[i];
+    }
+
+    for (int i = 0; i < 4; i++) {
+        bary[i] /= s;
+    }
+
+    return 0;
+}
+
+int initelem(const float* node, const int* elem, int ne, const float* srcpos, float* bary) {
+    // mesh_initelem, src/mmc_mesh.c:1060-1090
+    for (int i = 0; i < ne; i++) {
+        double pmin[3] = {VERY_BIG, VERY_BIG, VERY_BIG}, pmax[3] = { -VERY_BIG, -VERY_BIG, -VERY_BIG};
+        const int* ee = elem + 4 * (size_t)i;
+
+        for (int j = 0; j < 4; j++) {
+            const float* p = nd(node, ee[j]);
+
+            for (int k = 0; k < 3; k++) {
+                pmin[k] = std::min(pmin[k], (double)p[k]);
+                pmax[k] = std::max(pmax[k], (double)p[k]);
+            }
+        }
+
+        if (srcpos[0] <= pmax[0] && srcpos[0] >= pmin[0] && srcpos[1] <= pmax[1] && srcpos[1] >= pmin[1] &&
+                srcpos[2] <= pmax[2] && srcpos[2] >= pmin[2]) {
+            if (barycentric(node, elem, ne, i + 1, bary, srcpos) == 0) {
+                return i + 1;
+            }
+        }
+    }
+
+    return 0;
+}
+
+double getreff(double n_in, double n_out) {
+    // mesh_getreff, src/mmc_mesh.c:2305-2334
+    double oc = asin(1.0 / n_in);
+    const double count = 1000.0, ostep = (M_PI / (2.0 * count));
+    double r_phi = 0.0, r_j = 0.0;
+
+    for (int i = 0; i < count; i++) {
+        double o = i * ostep, coso = cos(o), r_fres;
+
+        if (o < oc) {
+            double cosop = n_in * sin(o);
+            cosop = sqrt(1. - cosop * cosop);
+            double tmp = (n_in * cosop - n_out * coso) / (n_in * cosop + n_out * coso);
+            r_fres = 0.5 * tmp * tmp;
+            tmp = (n_in * coso - n_out * cosop) / (n_in * coso + n_out * cosop);
+            r_fres += 0.5 * tmp * tmp;
+        } else {
+            r_fres = 1.f;
+        }
+
+        r_phi += 2.0 * sin(o) * coso * r_fres;
+        r_j += 3.0 * sin(o) * coso * coso * r_fres;
+    }
+
+    r_phi *= ostep;
+    r_j *= ostep;
+    return (r_phi + r_j) / (2.0 - r_phi + r_j);
+}
+
+struct Cfg {              // validated copy of mmcb_config
+    mmcb_config c;
+    int maxgate = 1;
+    int datalen = 0, reclen = 0;
+    int dim[3] = {0, 0, 0};
+    unsigned int crop0[3] = {0, 0, 0};
+    std::vector<float> pattern, detpos;
+};
+
+int validate(const mmcb_config* in, const mmcb_mesh* mesh, Cfg& o) {
+    // mcx_validatecfg (src/mmc_utils.c:3500-3566) + mcx_prep (:3724-3736)
+    if (!in || !mesh) {
+        return fail(MMCB_ERR_INPUT, "null config or mesh");
+    }
+
+    o.c = *in;
+    mmcb_config& c = o.c;
+
+    if (c.nphoton == 0 && c.seed != MMCB_SEED_FROM_FILE) {
+        return fail(MMCB_ERR_INPUT, "cfg.nphoton must be a positive number");
+    }
+
+    if (c.tstart > c.tend || c.tstep == 0.f) {
+        return fail(MMCB_ERR_INPUT, "incorrect time gate settings or missing tstart/tend/tstep fields");
+    }
+
+    if (c.tstep > c.tend - c.tstart) {
+        c.tstep = c.tend - c.tstart;
+    }
+
+    if (fabs(c.srcdir[0] * c.srcdir[0] + c.srcdir[1] * c.srcdir[1] + c.srcdir[2] * c.srcdir[2] - 1.f) > 1e-4) {
+        return fail(MMCB_ERR_INPUT, "field 'srcdir' must be a unitary vector (tolerance is 1e-4)");
+    }
+
+    if (c.tend <= c.tstart) {
+        return fail(MMCB_ERR_INPUT, "field 'tend' must be greater than field 'tstart'");
+    }
+
+    o.maxgate = (int)((c.tend - c.tstart) / c.tstep + 0.5);
+    c.tend = c.tstart + c.tstep * o.maxgate;
+
+    if (c.srcnum < 1) {
+        c.srcnum = 1;
+    }
+
+    if (c.srcnum > MMCB_MAX_SRCNUM) {
+        return fail(MMCB_ERR_LIMIT, "at most %d simultaneous patterns are supported", MMCB_MAX_SRCNUM);
+    }
+
+    if (c.srctype == MMCB_SRC_PATTERN && c.srcpattern == NULL) {
+        return fail(MMCB_ERR_INPUT, "the 'srcpattern' field can not be empty when your 'srctype' is 'pattern'");
+    }
+
+    if (c.srctype < 0 || c.srctype > MMCB_SRC_SLIT) {
+        return fail(MMCB_ERR_INPUT, "source type %d is not supported on the GPU path", c.srctype);
+    }
+
+    if (c.srcnum > 1 && c.seed == MMCB_SEED_FROM_FILE) {
+        return fail(MMCB_ERR_INPUT, "multiple source simulation is currently not supported under replay mode");
+    }
+
+    if (c.seed == MMCB_SEED_FROM_FILE && (!c.photonseed || !c.replayweight || !c.replaytime)) {
+        return fail(MMCB_ERR_INPUT, "replay needs photonseed, replayweight and replaytime");
+    }
+
+    if (c.method == MMCB_RT_BADOUEL) {
+        c.method = MMCB_RT_BLBADOUEL;      // the GPU path offers the branch-less variant (src/mmc_utils.c:3542-3544)
+    }
+
+    if (c.method != MMCB_RT_BLBADOUEL && c.method != MMCB_RT_BLBADOUEL_GRID) {
+        return fail(MMCB_ERR_INPUT, "ray tracer %d is not built into this library yet (use 's' or 'g')", c.method);
+    }
+
+    if (c.method == MMCB_RT_BLBADOUEL_GRID) {
+        c.basisorder = 0;
+
+        if (!(c.steps > 0.f)) {
+            return fail(MMCB_ERR_INPUT, "dual-grid voxel size must be positive");
+        }
+    }
+
+    if (c.detnum > MMCB_MAX_DET) {
+        return fail(MMCB_ERR_LIMIT, "at most %d point detectors are supported", MMCB_MAX_DET);
+    }
+
+    if (c.detnum > 0 && !c.detpos) {
+        return fail(MMCB_ERR_INPUT, "detnum>0 but detpos is NULL");
+    }
+
+    if (c.respin < 1) {
+        c.respin = 1;
+    }
+
+    if (c.roulettesize <= 0.f) {
+        c.roulettesize = 10.f;
+    }
+
+    if (c.unitinmm <= 0.f) {
+        c.unitinmm = 1.f;
+    }
+
+    if (c.srctype == MMCB_SRC_PATTERN) {
+        size_t n = (size_t)((int)c.srcparam1[3]) * (size_t)((int)c.srcparam2[3]) * c.srcnum;
+        o.pattern.assign(c.srcpattern, c.srcpattern + n);
+    }
+
+    if (c.detnum > 0) {
+        o.detpos.assign(c.detpos, c.detpos + 4 * (size_t)c.detnum);
+    }
+
+    return 0;
+}
+
+int prepare_mesh(const mmcb_mesh* in, Cfg& cfg, PrepMesh& m) {
+    mmcb_config& c = cfg.c;
+
+    if (in->nn <= 0 || in->ne <= 0 || !in->node || !in->elem || !in->type || !in->med || in->prop < 1) {
+        return fail(MMCB_ERR_MESH, "mesh is missing");
+    }
+
+    m.nn = in->nn;
+    m.ne = in->ne;
+    m.prop = in->prop;
+    m.node.assign(in->node, in->node + 3 * (size_t)in->nn);
+    m.elem.assign(in->elem, in->elem + 4 * (size_t)in->ne);
+    m.type.assign(in->type, in->type + in->ne);
+
+    for (size_t i = 0; i < m.elem.size(); i++)
+        if (m.elem[i] < 1 || m.elem[i] > m.nn) {
+            return fail(MMCB_ERR_MESH, "element %zu references node %d outside 1..%d", i / 4 + 1, m.elem[i], m.nn);
+        }
+
+    // mesh_srcdetelem, src/mmc_mesh.c:390-427
+    for (int i = 0; i < m.ne; i++) {
+        if (m.type[i] == -1) {
+            m.srcelem.push_back(i + 1);
+
+            if (!m.e0_from_src) {
+                m.e0_from_src = i + 1;
+            }
+
+            m.type[i] = 0;
+        } else if (m.type[i] == -2) {
+            m.detelem.push_back(i + 1);
+            m.isextdet = 1;
+        }
+    }
+
+    if (m.isextdet) {
+        c.detnum = 0;      // wide-field detectors suppress point detectors (:406)
+    }
+
+    // mesh_loadmedia, src/mmc_mesh.c:511-547
+    m.med.assign(in->med, in->med + in->prop + 1);
+    m.med[0] = {0.f, 0.f, 1.f, c.nout};
+
+    if (m.isextdet) {
+        m.med.push_back(m.med[0]);
+
+        for (int i = 0; i < m.ne; i++)
+            if (m.type[i] == -2) {
+                m.type[i] = m.prop + 1;
+            }
+    }
+
+    for (int i = 0; i < m.ne; i++)
+        if (m.type[i] < 0 || m.type[i] > m.prop + m.isextdet) {
+            return fail(MMCB_ERR_MESH, "element %d has medium label %d outside 0..%d", i + 1, m.type[i], m.prop);
+        }
+
+    if (c.unitinmm != 1.f)
+        for (int i = 1; i <= m.prop; i++) {
+            m.med[i].mus *= c.unitinmm;
+            m.med[i].mua *= c.unitinmm;
+        }
+
+    m.evol.resize(m.ne);
+    m.nvol.assign(m.nn, 0.f);
+
+    if (in->evol) {
+        // mesh_loadelemvol (src/mmc_mesh.c:723-761): volumes given => elements are used as they are (no node swap)
+        std::copy(in->evol, in->evol + m.ne, m.evol.begin());
+
+        for (int i = 0; i < m.ne; i++) {
+            if (m.type[i] == 0) {
+                continue;
+            }
+
+            for (int j = 0; j < 4; j++) {
+                m.nvol[m.elem[4 * (size_t)i + j] - 1] += m.evol[i] * 0.25f;
+            }
+        }
+    } else {
+        volumes(m.nn, m.node.data(), m.ne, m.elem.data(), m.type.data(), m.evol.data(), m.nvol.data());
+    }
+
+    if (in->nvol) {
+        std::copy(in->nvol, in->nvol + m.nn, m.nvol.begin());
+    }
+
+    m.facenb.resize(4 * (size_t)m.ne);
+
+    if (in->facenb) {
+        for (size_t i = 0; i < m.facenb.size(); i++) {
+            m.facenb[i] = in->facenb[i] > 0 ? in->facenb[i] : 0;
+        }
+    } else {
+        facenb_build(m.ne, m.elem.data(), m.facenb.data());
+    }
+
+    // mcx_prep: detector bookkeeping (src/mmc_utils.c:3729-3736)
+    if (c.issavedet && c.detnum == 0 && m.isextdet == 0) {
+        c.issavedet = 0;
+    }
+
+    if (!c.issavedet) {
+        c.ismomentum = 0;
+        c.issaveexit = 0;
+        c.issaveseed = 0;
+    }
+
+    if (c.e0 == 0 && m.e0_from_src) {
+        c.e0 = m.e0_from_src;
+    }
+
+    // tracer_prep: initial element for point-like sources, src/mmc_mesh.c:1324-1329
+    if (c.srctype == MMCB_SRC_PENCIL || c.srctype == MMCB_SRC_ISOTROPIC || c.srctype == MMCB_SRC_CONE || c.srctype == MMCB_SRC_ARCSINE) {
+        float bary[4];
+
+        if (c.e0 <= 0 || barycentric(m.node.data(), m.elem.data(), m.ne, c.e0, bary, c.srcpos)) {
+            c.e0 = initelem(m.node.data(), m.elem.data(), m.ne, c.srcpos, bary);
+
+            if (c.e0 == 0) {
+                return fail(MMCB_ERR_MESH, "initial element does not enclose the source!");
+            }
+        }
+    } else if (c.e0 <= 0 && m.srcelem.empty()) {
+        return fail(MMCB_ERR_MESH, "area sources need an initial element or elements labelled -1");
+    }
+
+    if (c.e0 > m.ne) {
+        return fail(MMCB_ERR_MESH, "initial element index exceeds total element count");
+    }
+
+    // surface nodal volumes x 2/(1+Reff), src/mmc_mesh.c:1344-1386
+    if (c.isnormalized == 1 && c.method != MMCB_RT_BLBADOUEL_GRID && c.basisorder) {
+        std::vector<float> Reff(m.prop + 2, 0.f);
+
+        if (c.isreflect) {
+            for (int i = 1; i <= m.prop; i++) {
+                for (int j = 1; j < i; j++)
+                    if (m.med[j].n == m.med[i].n) {
+                        Reff[i] = Reff[j];
+                        break;
+                    }
+
+                if (Reff[i] == 0.f) {
+                    Reff[i] = (float)getreff(m.med[i].n, m.med[0].n);
+                }
+            }
+        }
+
+        for (int i = 0; i < m.ne; i++) {
+            const int* ee = &m.elem[4 * (size_t)i], *enb = &m.facenb[4 * (size_t)i];
+
+            for (int j = 0; j < 4; j++)
+                if (enb[j] == 0)
+                    for (int k = 0; k < 3; k++) {
+                        int nid = ee[OUT[IFACEORDER[j]][k]] - 1;
+
+                        if (m.nvol[nid] > 0.f && m.type[i] >= 0) {
+                            m.nvol[nid] *= -(2.f / (1.0 + Reff[m.type[i] > m.prop ? 0 : m.type[i]]));
+                        }
+                    }
+        }
+
+        for (int i = 0; i < m.nn; i++)
+            if (m.nvol[i] < 0.f) {
+                m.nvol[i] = -m.nvol[i];
+            }
+    }
+
+    // exterior faces numbered -1..-nf, src/mmc_mesh.c:1466-1474
+    m.nf = 0;
+
+    for (size_t i = 0; i < m.facenb.size(); i++)
+        if (m.facenb[i] == 0) {
+            m.facenb[i] = -(++m.nf);
+        }
+
+    // dual grid, src/mmc_mesh.c:349-381
+    for (int k = 0; k < 3; k++) {
+        m.nmin[k] = VERY_BIG;
+        m.nmax[k] = -VERY_BIG;
+    }
+
+    for (int i = 0; i < m.nn; i++)
+        for (int k = 0; k < 3; k++) {
+            m.nmin[k] = std::min(m.nmin[k], m.node[3 * (size_t)i + k]);
+            m.nmax[k] = std::max(m.nmax[k], m.node[3 * (size_t)i + k]);
+        }
+
+    for (int k = 0; k < 3; k++) {
+        m.nmin[k] -= EPSF;
+        m.nmax[k] += EPSF;
+    }
+
+    if (c.method == MMCB_RT_BLBADOUEL_GRID) {
+        for (int k = 0; k < 3; k++) {
+            cfg.dim[k] = (int)((m.nmax[k] - m.nmin[k]) / c.steps) + 1;
+        }
+
+        cfg.crop0[0] = cfg.dim[0];
+        cfg.crop0[1] = cfg.dim[1] * cfg.dim[0];
+        cfg.crop0[2] = cfg.dim[1] * cfg.dim[0] * cfg.dim[2];
+        cfg.datalen = (int)cfg.crop0[2];
+    } else {
+        cfg.datalen = c.basisorder ? m.nn : m.ne;
+    }
+
+    cfg.reclen = (2 + (c.ismomentum > 0)) * m.prop + (c.issaveexit > 0) * 6 + 2;   // host record length (src/mmc_host.c:248)
+    return 0;
+}
+
+// BLB face planes (tracer_build, src/mmc_mesh.c:1572-1600) + neighbours/type/flags -> 96-byte records
+void build_records(const PrepMesh& m, const Cfg& cfg, std::vector<mmcb_tetrec>& rec, std::vector<float>& cent) {
+    const mmcb_config& c = cfg.c;
+    rec.resize(m.ne);
+    cent.resize(4 * (size_t)m.ne);
+
+    for (int i = 0; i < m.ne; i++) {
+        mmcb_tetrec& r = rec[i];
+        memset(&r, 0, sizeof(r));
+        const int* ee = &m.elem[4 * (size_t)i];
+        const float n_here = m.med[m.type[i]].n;
+
+        for (int j = 0; j < 4; j++) {
+            const float* a = nd(m.node.data(), ee[OUT[j][0]]), *b = nd(m.node.data(), ee[OUT[j][1]]), *cc = nd(m.node.data(), ee[OUT[j][2]]);
+            float AB[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, AC[3] = {cc[0] - a[0], cc[1] - a[1], cc[2] - a[2]};
+            float N[3] = {AB[1]* AC[2] - AB[2]* AC[1], AB[2]* AC[0] - AB[0]* AC[2], AB[0]* AC[1] - AB[1]* AC[0]};
+            float Rn2 = 1.f / sqrt(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
+            N[0] *= Rn2;
+            N[1] *= Rn2;
+            N[2] *= Rn2;
+            r.nx[j] = N[0];
+            r.ny[j] = N[1];
+            r.nz[j] = N[2];
+            r.d[j] = N[0] * a[0] + N[1] * a[1] + N[2] * a[2];
+            int nb = m.facenb[4 * (size_t)i + FACEORDER[j]];
+            r.nb[j] = nb;
+            // when does crossing face j call reflectray?  src/mmc_core.cl:1957-1958
+            bool refl;
+
+            if (nb <= 0) {
+                refl = !((n_here == c.nout && c.isreflect != MMCB_BC_MIRROR) || c.isreflect == MMCB_BC_ABSORB_EXTERIOR);
+            } else {
+                refl = (m.med[m.type[nb - 1]].n != n_here);
+            }
+
+            if (refl) {
+                r.flags |= MMCB_F_REFLECT(j);
+            }
+
+            if (nb > 0) {
+                if (m.type[i] != 0 && m.type[nb - 1] == 0) {
+                    r.flags |= MMCB_F_TO_VOID(j);
+                }
+
+                if (m.type[i] == 0 && m.type[nb - 1] != 0) {
+                    r.flags |= MMCB_F_FROM_VOID(j);
+                }
+            }
+        }
+
+        r.type = m.type[i];
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+
+        for (int j = 0; j < 4; j++) {
+            const float* q = nd(m.node.data(), ee[j]);
+            cx += q[0];
+            cy += q[1];
+            cz += q[2];
+        }
+
+        cent[4 * (size_t)i] = cx * 0.25f;
+        cent[4 * (size_t)i + 1] = cy * 0.25f;
+        cent[4 * (size_t)i + 2] = cz * 0.25f;
+        cent[4 * (size_t)i + 3] = 0.f;
+    }
+}
+
+template <typename T>
+int dev_alloc_copy(T** dptr, const T* host, size_t n) {
+    *dptr = NULL;
+
+    if (n == 0) {
+        return 0;
+    }
+
+    CU(cudaMalloc((void**)dptr, n * sizeof(T)));
+
+    if (host) {
+        CU(cudaMemcpy(*dptr, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    } else {
+        CU(cudaMemset(*dptr, 0, n * sizeof(T)));
+    }
+
+    return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// session
+// ---------------------------------------------------------------------------------------------------
+struct mmcb_session {
+    int device = 0;
+    Cfg cfg;
+    PrepMesh mesh;
+    mmcb_kparam kp;
+    mmcb_kargs ka;
+    cudaStream_t stream = NULL;
+    cudaEvent_t ev0 = NULL, ev1 = NULL;
+    float last_ms = 0.f, total_ms = 0.f;
+    int grid = 0, block = 128, nthread = 0;
+    size_t smem = 0;
+    bool isgrid = false, isdet = false, isgeneral = false;
+    size_t fieldlen = 0, efieldlen = 0;     // output volume / kernel accumulator volume (differ for nodal BLB)
+    bool acc_double = true, field_external = false;
+    // device allocations
+    mmcb_tetrec* d_tet = NULL;
+    float4* d_cent = NULL;
+    float* d_node = NULL;
+    int* d_elem = NULL;
+    int* d_srcelem = NULL;
+    float4* d_med = NULL;
+    float* d_pattern = NULL;
+    uint32_t* d_seeds = NULL;
+    unsigned long long* d_replayseed = NULL;
+    float* d_replayweight = NULL, *d_replaytime = NULL;
+    void* d_field = NULL;
+    double* d_dref = NULL;
+    float* d_detected = NULL;
+    unsigned int* d_detcount = NULL;
+    unsigned long long* d_detseed = NULL;
+    float* d_traj = NULL;
+    unsigned int* d_trajcount = NULL;
+    double* d_energy = NULL, *d_raytet = NULL;
+    unsigned long long* d_counter = NULL;
+    std::vector<uint32_t> hseeds;
+    uint64_t launched = 0;
+};
+
+static int session_free(mmcb_session* s) {
+    if (!s) {
+        return 0;
+    }
+
+    cudaSetDevice(s->device);
+    cudaFree(s->d_tet);
+    cudaFree(s->d_cent);
+    cudaFree(s->d_node);
+    cudaFree(s->d_elem);
+    cudaFree(s->d_srcelem);
+    cudaFree(s->d_med);
+    cudaFree(s->d_pattern);
+    cudaFree(s->d_seeds);
+    cudaFree(s->d_replayseed);
+    cudaFree(s->d_replayweight);
+    cudaFree(s->d_replaytime);
+
+    if (!s->field_external) {
+        cudaFree(s->d_field);
+    }
+
+    cudaFree(s->d_dref);
+    cudaFree(s->d_detected);
+    cudaFree(s->d_detcount);
+    cudaFree(s->d_detseed);
+    cudaFree(s->d_traj);
+    cudaFree(s->d_trajcount);
+    cudaFree(s->d_energy);
+    cudaFree(s->d_raytet);
+    cudaFree(s->d_counter);
+
+    if (s->ev0) {
+        cudaEventDestroy(s->ev0);
+    }
+
+    if (s->ev1) {
+        cudaEventDestroy(s->ev1);
+    }
+
+    if (s->stream) {
+        cudaStreamDestroy(s->stream);
+    }
+
+    delete s;
+    return 0;
+}
+
+static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_mesh* meshin, int device) {
+    int rc = validate(cfgin, meshin, s->cfg);
+
+    if (rc) {
+        return rc;
+    }
+
+    rc = prepare_mesh(meshin, s->cfg, s->mesh);
+
+    if (rc) {
+        return rc;
+    }
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+
+    if (e != cudaSuccess || ndev == 0) {
+        return fail(MMCB_ERR_CUDA, "no CUDA device is available (%s); mmc_b200 has no CPU fallback", cudaGetErrorString(e));
+    }
+
+    if (device < 0 || device >= ndev) {
+        return fail(MMCB_ERR_CUDA, "GPU ID must be within 0..%d", ndev - 1);
+    }
+
+    s->device = device;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s->ev0));
+    CU(cudaEventCreate(&s->ev1));
+    const mmcb_config& c = s->cfg.c;
+    const PrepMesh& m = s->mesh;
+    s->acc_double = mmcb_k_acc_is_double() != 0;
+    s->isgrid = (c.method == MMCB_RT_BLBADOUEL_GRID);
+    s->isdet = c.issavedet != 0;
+    s->isgeneral = !(c.srctype == MMCB_SRC_PENCIL || c.srctype == MMCB_SRC_ISOTROPIC) || c.srcnum > 1 ||
+                   c.seed == MMCB_SEED_FROM_FILE || c.savetraj || c.issaveref;
+    // tables
+    std::vector<mmcb_tetrec> rec;
+    std::vector<float> cent;
+    build_records(m, s->cfg, rec, cent);
+    rc = dev_alloc_copy(&s->d_tet, rec.data(), rec.size());
+
+    if (rc) {
+        return rc;
+    }
+
+    if ((rc = dev_alloc_copy((float**)&s->d_cent, cent.data(), cent.size()))) {
+        return rc;
+    }
+
+    if ((rc = dev_alloc_copy(&s->d_node, m.node.data(), m.node.size()))) {
+        return rc;
+    }
+
+    if ((rc = dev_alloc_copy(&s->d_elem, m.elem.data(), m.elem.size()))) {
+        return rc;
+    }
+
+    if ((rc = dev_alloc_copy(&s->d_srcelem, m.srcelem.data(), m.srcelem.size()))) {
+        return rc;
+    }
+
+    if ((rc = dev_alloc_copy((mmcb_medium**)&s->d_med, m.med.data(), m.med.size()))) {
+        return rc;
+    }
+
+    if ((rc = dev_alloc_copy(&s->d_pattern, s->cfg.pattern.data(), s->cfg.pattern.size()))) {
+        return rc;
+    }
+
+    // accumulators
+    const int srcnum = c.srcnum;
+    s->fieldlen = (size_t)s->cfg.datalen * s->cfg.maxgate * srcnum;
+    size_t framelen = s->isgrid ? (size_t)s->cfg.crop0[2] : (size_t)m.ne;
+    s->efieldlen = framelen * s->cfg.maxgate * srcnum;
+
+    if (s->efieldlen >= 0xFFFFFFFFull) {
+        return fail(MMCB_ERR_LIMIT, "output volume of %zu entries exceeds the 32-bit index range of the kernel", s->efieldlen);
+    }
+
+    CU(cudaMalloc(&s->d_field, s->efieldlen * (s->acc_double ? 8 : 4)));
+    CU(cudaMemset(s->d_field, 0, s->efieldlen * (s->acc_double ? 8 : 4)));
+
+    if (c.issaveref) {
+        if ((rc = dev_alloc_copy(&s->d_dref, (const double*)NULL, (size_t)m.nf * s->cfg.maxgate))) {
+            return rc;
+        }
+    }
+
+    const int devreclen = s->cfg.reclen - 1;      // kernel-side record (without detid)
+
+    if (s->isdet) {
+        if ((rc = dev_alloc_copy(&s->d_detected, (const float*)NULL, (size_t)c.maxdetphoton * s->cfg.reclen))) {
+            return rc;
+        }
+
+        if (c.issaveseed && (rc = dev_alloc_copy(&s->d_detseed, (const unsigned long long*)NULL, (size_t)c.maxdetphoton * 2))) {
+            return rc;
+        }
+    }
+
+    if ((rc = dev_alloc_copy(&s->d_detcount, (const unsigned int*)NULL, 1))) {
+        return rc;
+    }
+
+    if (c.savetraj) {
+        if ((rc = dev_alloc_copy(&s->d_traj, (const float*)NULL, (size_t)c.maxjumpdebug * MMCB_DEBUG_REC))) {
+            return rc;
+        }
+    }
+
+    if ((rc = dev_alloc_copy(&s->d_trajcount, (const unsigned int*)NULL, 1))) {
+        return rc;
+    }
+
+    if ((rc = dev_alloc_copy(&s->d_energy, (const double*)NULL, 2 * MMCB_MAX_SRCNUM))) {
+        return rc;
+    }
+
+    if ((rc = dev_alloc_copy(&s->d_raytet, (const double*)NULL, 1))) {
+        return rc;
+    }
+
+    if ((rc = dev_alloc_copy(&s->d_counter, (const unsigned long long*)NULL, 1))) {
+        return rc;
+    }
+
+    if (c.seed == MMCB_SEED_FROM_FILE) {
+        if ((rc = dev_alloc_copy(&s->d_replayseed, (const unsigned long long*)c.photonseed, (size_t)c.nphoton * 2))) {
+            return rc;
+        }
+
+        if ((rc = dev_alloc_copy(&s->d_replayweight, c.replayweight, (size_t)c.nphoton))) {
+            return rc;
+        }
+
+        if ((rc = dev_alloc_copy(&s->d_replaytime, c.replaytime, (size_t)c.nphoton))) {
+            return rc;
+        }
+    }
+
+    // launch shape: persistent grid = resident CTAs per SM x SM count (the reference sizes to 64 thr x 32 x #SM, src/mmc_cu_host.cu:159-163)
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    s->block = (c.nblocksize > 0) ? c.nblocksize : 128;
+    s->block = std::max(32, (s->block / 32) * 32);
+    s->smem = sizeof(float4) * m.med.size() + (s->isdet ? sizeof(float) * (size_t)devreclen * s->block : 0);
+
+    if (s->smem > (size_t)prop.sharedMemPerBlockOptin) {
+        return fail(MMCB_ERR_LIMIT, "media table and detector records need %zu bytes of shared memory, device offers %zu", s->smem, (size_t)prop.sharedMemPerBlockOptin);
+    }
+
+    int bps = 0;
+    CUK(mmcb_k_occupancy(s->block, s->smem, s->isgrid, s->isdet, s->isgeneral, &bps));
+
+    if (bps < 1) {
+        return fail(MMCB_ERR_CUDA, "kernel cannot be resident with block=%d smem=%zu", s->block, s->smem);
+    }
+
+    if (c.nthread > 0) {
+        s->grid = std::max(1, c.nthread / s->block);
+    } else {
+        s->grid = bps * prop.multiProcessorCount;
+    }
+
+    s->nthread = s->grid * s->block;
+    CU(cudaMalloc(&s->d_seeds, sizeof(uint32_t) * 4 * (size_t)s->nthread));
+    // kernel parameters
+    mmcb_kparam& k = s->kp;
+    memset(&k, 0, sizeof(k));
+    memcpy(k.srcpos, c.srcpos, sizeof(k.srcpos));
+    memcpy(k.srcdir, c.srcdir, sizeof(k.srcdir));
+    memcpy(k.srcparam1, c.srcparam1, sizeof(k.srcparam1));
+    memcpy(k.srcparam2, c.srcparam2, sizeof(k.srcparam2));
+    k.srctype = c.srctype;
+    k.srcnum = srcnum;
+    k.srcelemlen = (int)m.srcelem.size();
+    k.e0 = c.e0;
+    k.focus = c.srcdir[3];
+    k.tstart = c.tstart;
+    k.tend = c.tend;
+    k.Rtstep = 1.f / c.tstep;
+    k.maxgate = s->cfg.maxgate;
+    k.isreflect = c.isreflect;
+    k.isspecular = c.isspecular;
+    k.voidtime = c.voidtime;
+    k.isextdet = m.isextdet;
+    k.outputtype = c.outputtype;
+    k.method = c.method;
+    k.basisorder = c.basisorder;
+    k.minenergy = c.minenergy;
+    k.roulettesize = c.roulettesize;
+    k.nout = c.nout;
+    k.doroulette = ((c.tend - c.tstart) * k.Rtstep <= 1.f);
+    k.nn = m.nn;
+    k.ne = m.ne;
+    k.nf = m.nf;
+    k.maxmedia = m.prop;
+    k.framelen = (unsigned int)framelen;
+    memcpy(k.nmin, m.nmin, sizeof(k.nmin));
+    k.dstep = s->isgrid ? 1.f / c.steps : 1.f;
+    memcpy(k.crop0, s->cfg.crop0, sizeof(k.crop0));
+    k.issavedet = c.issavedet;
+    k.ismomentum = c.ismomentum;
+    k.issaveexit = c.issaveexit;
+    k.issaveseed = c.issaveseed;
+    k.issaveref = c.issaveref;
+    k.detnum = c.detnum;
+    k.reclen = devreclen;
+    k.maxdetphoton = c.maxdetphoton;
+    k.isreplay = (c.seed == MMCB_SEED_FROM_FILE);
+    k.savetraj = c.savetraj;
+    k.maxjumpdebug = c.maxjumpdebug;
+    k.schedule = c.schedule;
+    k.nmedia = (int)m.med.size();
+    mmcb_kargs& a = s->ka;
+    memset(&a, 0, sizeof(a));
+    a.tet = s->d_tet;
+    a.cent = s->d_cent;
+    a.node = s->d_node;
+    a.elem = s->d_elem;
+    a.srcelem = s->d_srcelem;
+    a.med = s->d_med;
+    a.srcpattern = s->d_pattern;
+    a.seeds = s->d_seeds;
+    a.replayseed = s->d_replayseed;
+    a.replayweight = s->d_replayweight;
+    a.replaytime = s->d_replaytime;
+    a.field = s->d_field;
+    a.dref = s->d_dref;
+    a.detected = s->d_detected;
+    a.detcount = s->d_detcount;
+    a.detseed = s->d_detseed;
+    a.traj = s->d_traj;
+    a.trajcount = s->d_trajcount;
+    a.energy = s->d_energy;
+    a.raytet = s->d_raytet;
+    a.photon_counter = s->d_counter;
+    return 0;
+}
+
+extern "C" {
+
+int mmcb_version(void) {
+    return MMCB_VERSION;
+}
+
+const char* mmcb_last_error(void) {
+    return g_err.c_str();
+}
+
+void mmcb_host_seeds(int seed, size_t skip, size_t count, uint32_t* out) {
+    GlibcRand g((unsigned int)seed);
+
+    for (size_t i = 0; i < skip; i++) {
+        g.next();
+    }
+
+    for (size_t i = 0; i < count; i++) {
+        out[i] = g.next();
+    }
+}
+
+int mmcb_rng_selftest(const uint32_t* seeds4, int nstream, int ndraw, float* out, uint64_t* state_out) {
+    if (!seeds4 || !out || nstream <= 0 || ndraw <= 0) {
+        return fail(MMCB_ERR_INPUT, "bad argument");
+    }
+
+    uint32_t* ds = NULL;
+    float* dout = NULL;
+    unsigned long long* dst = NULL;
+    CU(cudaMalloc(&ds, sizeof(uint32_t) * 4 * (size_t)nstream));
+    CU(cudaMalloc(&dout, sizeof(float) * (size_t)nstream * ndraw));
+    CU(cudaMalloc(&dst, sizeof(unsigned long long) * 2 * (size_t)nstream));
+    CU(cudaMemcpy(ds, seeds4, sizeof(uint32_t) * 4 * (size_t)nstream, cudaMemcpyHostToDevice));
+    CUK(mmcb_k_rng(ds, nstream, ndraw, dout, dst, 0));
+    CU(cudaMemcpy(out, dout, sizeof(float) * (size_t)nstream * ndraw, cudaMemcpyDeviceToHost));
+
+    if (state_out) {
+        CU(cudaMemcpy(state_out, dst, sizeof(uint64_t) * 2 * (size_t)nstream, cudaMemcpyDeviceToHost));
+    }
+
+    cudaFree(ds);
+    cudaFree(dout);
+    cudaFree(dst);
+    return 0;
+}
+
+int mmcb_list_gpu(mmcb_gpuinfo* info, int maxcount) {
+    // mcx_list_cu_gpu, src/mmc_cu_host.cu:108-198
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+
+    if (e != cudaSuccess) {
+        g_err = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+        return 0;
+    }
+
+    for (int i = 0; i < ndev && i < maxcount; i++) {
+        cudaDeviceProp dp;
+
+        if (cudaGetDeviceProperties(&dp, i) != cudaSuccess) {
+            return fail(MMCB_ERR_CUDA, "cudaGetDeviceProperties failed");
+        }
+
+        mmcb_gpuinfo& g = info[i];
+        memset(&g, 0, sizeof(g));
+        snprintf(g.name, sizeof(g.name), "%s", dp.name);
+        g.id = i + 1;
+        g.devcount = ndev;
+        g.major = dp.major;
+        g.minor = dp.minor;
+        g.globalmem = dp.totalGlobalMem;
+        g.constmem = dp.totalConstMem;
+        g.sharedmem = dp.sharedMemPerBlock;
+        g.regcount = dp.regsPerBlock;
+        g.clock = dp.clockRate;
+        g.sm = dp.multiProcessorCount;
+        g.core = dp.multiProcessorCount * 128;
+        g.maxmpthread = dp.maxThreadsPerMultiProcessor;
+        g.autoblock = 128;
+        g.autothread = (size_t)g.autoblock * (dp.maxThreadsPerMultiProcessor / 2 / g.autoblock) * g.sm;
+        g.maxgate = 0;
+    }
+
+    return ndev;
+}
+
+int mmcb_mesh_volumes(int nn, const float* node, int ne, int* elem_inout, const int* type, float* evol, float* nvol) {
+    if (!node || !elem_inout || !evol || !nvol) {
+        return fail(MMCB_ERR_INPUT, "null argument");
+    }
+
+    volumes(nn, node, ne, elem_inout, type, evol, nvol);
+    return 0;
+}
+
+int mmcb_mesh_facenb(int ne, const int* elem, int* facenb) {
+    if (!elem || !facenb) {
+        return fail(MMCB_ERR_INPUT, "null argument");
+    }
+
+    facenb_build(ne, elem, facenb);
+    return 0;
+}
+
+int mmcb_mesh_initelem(int nn, const float* node, int ne, const int* elem, const float* srcpos, float* bary4) {
+    (void)nn;
+    float b[4];
+    int e0 = initelem(node, elem, ne, srcpos, bary4 ? bary4 : b);
+    return e0;
+}
+
+int mmcb_query_sizes(const mmcb_config* cfg, const mmcb_mesh* mesh, mmcb_sizes* sz) {
+    Cfg c;
+    PrepMesh m;
+    int rc = validate(cfg, mesh, c);
+
+    if (rc) {
+        return rc;
+    }
+
+    if ((rc = prepare_mesh(mesh, c, m))) {
+        return rc;
+    }
+
+    sz->maxgate = c.maxgate;
+    sz->datalen = c.datalen;
+    sz->reclen = c.reclen;
+    sz->nf = m.nf;
+    sz->srcnum = c.c.srcnum;
+    memcpy(sz->dim, c.dim, sizeof(sz->dim));
+    sz->fieldlen = (size_t)c.datalen * c.maxgate * c.c.srcnum;
+    return 0;
+}
+
+mmcb_session* mmcb_create(const mmcb_config* cfg, const mmcb_mesh* mesh, int device) {
+    mmcb_session* s = new mmcb_session();
+    int rc = session_build(s, cfg, mesh, device);
+
+    if (rc) {
+        std::string keep = g_err;
+        session_free(s);
+        g_err = keep;
+        return NULL;
+    }
+
+    return s;
+}
+
+void mmcb_destroy(mmcb_session* s) {
+    session_free(s);
+}
+
+int mmcb_get_sizes(mmcb_session* s, mmcb_sizes* sz) {
+    if (!s || !sz) {
+        return fail(MMCB_ERR_INPUT, "null argument");
+    }
+
+    sz->maxgate = s->cfg.maxgate;
+    sz->datalen = s->cfg.datalen;
+    sz->reclen = s->cfg.reclen;
+    sz->nf = s->mesh.nf;
+    sz->srcnum = s->cfg.c.srcnum;
+    memcpy(sz->dim, s->cfg.dim, sizeof(sz->dim));
+    sz->fieldlen = s->fieldlen;
+    return 0;
+}
+
+int mmcb_set_field_buffer(mmcb_session* s, void* device_ptr) {
+    if (!s || !device_ptr) {
+        return fail(MMCB_ERR_INPUT, "null argument");
+    }
+
+    CU(cudaSetDevice(s->device));
+
+    if (!s->field_external) {
+        cudaFree(s->d_field);
+    }
+
+    s->d_field = device_ptr;
+    s->ka.field = device_ptr;
+    s->field_external = true;
+    return 0;
+}
+
+int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int seed, int seed_offset, void* cuda_stream) {
+    if (!s) {
+        return fail(MMCB_ERR_INPUT, "null session");
+    }
+
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->stream;
+    // per-thread seeds: srand(seed); Pseed[j]=rand() (src/mmc_cu_host.cu:438,529-540); slices for ranks/respins
+    s->hseeds.resize(4 * (size_t)s->nthread);
+    mmcb_host_seeds(seed, (size_t)seed_offset * 4 * (size_t)s->nthread, s->hseeds.size(), s->hseeds.data());
+    CU(cudaMemcpyAsync(s->d_seeds, s->hseeds.data(), s->hseeds.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
+    s->kp.nphoton = nphoton;
+    s->kp.photon_offset = photon_offset;
+    s->kp.threadphoton = (int)(nphoton / (uint64_t)s->nthread);                 // src/mmc_cu_host.cu:425-429
+    s->kp.oddphotons = (int)(nphoton - (uint64_t)s->kp.threadphoton * s->nthread);
+    CUK(mmcb_k_upload_param(&s->kp, s->cfg.detpos.data(), s->cfg.c.detnum, st));
+    CU(cudaEventRecord(s->ev0, st));
+    CUK(mmcb_k_launch_photons(&s->ka, s->grid, s->block, s->smem, s->isgrid, s->isdet, s->isgeneral, st));
+    CU(cudaEventRecord(s->ev1, st));
+    s->launched += nphoton;
+    return 0;
+}
+
+int mmcb_sync(mmcb_session* s) {
+    if (!s) {
+        return fail(MMCB_ERR_INPUT, "null session");
+    }
+
+    CU(cudaSetDevice(s->device));
+    CU(cudaEventSynchronize(s->ev1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_ms = ms;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int mmcb_last_kernel_ms(mmcb_session* s, float* ms) {
+    if (!s || !ms) {
+        return fail(MMCB_ERR_INPUT, "null argument");
+    }
+
+    *ms = s->last_ms;
+    return 0;
+}
+
+int mmcb_get_devptrs(mmcb_session* s, mmcb_devptrs* p) {
+    if (!s || !p) {
+        return fail(MMCB_ERR_INPUT, "null argument");
+    }
+
+    p->field = s->d_field;
+    p->fieldlen = s->efieldlen;
+    p->field_is_double = s->acc_double;
+    p->energy = s->d_energy;
+    p->raytet = s->d_raytet;
+    p->detected = s->d_detected;
+    p->detcount = s->d_detcount;
+    p->reclen = s->cfg.reclen;
+    p->detseed = (uint64_t*)s->d_detseed;
+    p->dref = s->d_dref;
+    p->dreflen = (size_t)s->mesh.nf * s->cfg.maxgate;
+    return 0;
+}
+
+int mmcb_reset(mmcb_session* s) {
+    if (!s) {
+        return fail(MMCB_ERR_INPUT, "null session");
+    }
+
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemsetAsync(s->d_field, 0, s->efieldlen * (s->acc_double ? 8 : 4), s->stream));
+    CU(cudaMemsetAsync(s->d_energy, 0, sizeof(double) * 2 * MMCB_MAX_SRCNUM, s->stream));
+    CU(cudaMemsetAsync(s->d_raytet, 0, sizeof(double), s->stream));
+    CU(cudaMemsetAsync(s->d_detcount, 0, sizeof(unsigned int), s->stream));
+    CU(cudaMemsetAsync(s->d_trajcount, 0, sizeof(unsigned int), s->stream));
+
+    if (s->d_dref) {
+        CU(cudaMemsetAsync(s->d_dref, 0, sizeof(double) * (size_t)s->mesh.nf * s->cfg.maxgate, s->stream));
+    }
+
+    CU(cudaStreamSynchronize(s->stream));
+    s->launched = 0;
+    return 0;
+}
+
+// mesh_normalize, src/mmc_mesh.c:2154-2279, on the host copy of the volume
+static double normalize_field(const mmcb_session* s, double* W, double* dref, float Eabsorb, float Etotal, int pair) {
+    const mmcb_config& c = s->cfg.c;
+    const PrepMesh& m = s->mesh;
+    const int datalen = s->cfg.datalen, maxgate = s->cfg.maxgate, srcnum = c.srcnum;
+    double energydeposit = 0.f, energyelem, normalizor;
+
+    if (c.issaveref && dref) {
+        float nz = 1.f / Etotal;
+
+        for (size_t i = 0; i < (size_t)maxgate * m.nf; i++) {
+            dref[i] *= nz;
+        }
+    }
+
+    if (c.seed == MMCB_SEED_FROM_FILE && (c.outputtype == MMCB_OT_JACOBIAN || c.outputtype == MMCB_OT_WL || c.outputtype == MMCB_OT_WP)) {
+        float nz = 1.f / (1e-4f * c.nphoton);
+
+        if (c.outputtype == MMCB_OT_WL || c.outputtype == MMCB_OT_WP) {
+            nz = 1.f / Etotal;
+        }
+
+        for (int i = 0; i < maxgate; i++)
+            for (int j = 0; j < datalen; j++) {
+                W[((size_t)i * datalen + j)*srcnum + pair] *= nz;
+            }
+
+        return nz;
+    }
+
+    if (c.outputtype == MMCB_OT_ENERGY) {
+        normalizor = 1.f / Etotal;
+
+        for (int i = 0; i < maxgate; i++)
+            for (int j = 0; j < datalen; j++) {
+                W[((size_t)i * datalen + j)*srcnum + pair] *= normalizor;
+            }
+
+        return normalizor;
+    }
+
+    if (c.method == MMCB_RT_BLBADOUEL_GRID) {
+        normalizor = 1.0 / (Etotal * c.unitinmm * c.unitinmm * c.unitinmm);
+    } else if (c.basisorder) {
+        for (int i = 0; i < maxgate; i++)
+            for (int j = 0; j < datalen; j++)
+                if (m.nvol[j] > 0.f) {
+                    W[((size_t)i * datalen + j)*srcnum + pair] /= m.nvol[j];
+                }
+
+        for (int i = 0; i < m.ne; i++) {
+            const int* ee = &m.elem[4 * (size_t)i];
+            energyelem = 0.f;
+
+            for (int j = 0; j < maxgate; j++)
+                for (int k = 0; k < 4; k++) {
+                    float re_val = W[((size_t)j * m.nn + ee[k] - 1) * srcnum + pair];
+                    energyelem += re_val;
+                }
+
+            energydeposit += energyelem * m.evol[i] * m.med[m.type[i]].mua;
+        }
+
+        normalizor = Eabsorb / (Etotal * energydeposit * 0.25f);
+    } else {
+        for (int i = 0; i < datalen; i++)
+            for (int j = 0; j < maxgate; j++) {
+                energydeposit += W[((size_t)j * datalen + i) * srcnum + pair];
+            }
+
+        for (int i = 0; i < datalen; i++) {
+            energyelem = m.evol[i] * m.med[m.type[i]].mua;
+
+            for (int j = 0; j < maxgate; j++) {
+                W[((size_t)j * datalen + i) * srcnum + pair] /= energyelem;
+            }
+        }
+
+        normalizor = Eabsorb / (Etotal * energydeposit);
+    }
+
+    if (c.outputtype == MMCB_OT_FLUX) {
+        normalizor /= c.tstep;
+    }
+
+    for (int i = 0; i < maxgate; i++)
+        for (int j = 0; j < datalen; j++) {
+            W[((size_t)i * datalen + j)*srcnum + pair] *= normalizor;
+        }
+
+    return normalizor;
+}
+
+int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc, mmcb_output* out) {
+    if (!s || !out) {
+        return fail(MMCB_ERR_INPUT, "null argument");
+    }
+
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    const mmcb_config& c = s->cfg.c;
+    const PrepMesh& m = s->mesh;
+    double en[2 * MMCB_MAX_SRCNUM];
+    CU(cudaMemcpy(en, s->d_energy, sizeof(en), cudaMemcpyDeviceToHost));
+
+    for (int j = 0; j < MMCB_MAX_SRCNUM; j++) {
+        out->energytot[j] = energytot ? energytot[j] : en[j];
+        out->energyesc[j] = energyesc ? energyesc[j] : en[MMCB_MAX_SRCNUM + j];
+    }
+
+    CU(cudaMemcpy(&out->raytet, s->d_raytet, sizeof(double), cudaMemcpyDeviceToHost));
+    out->kernel_ms = s->last_ms;
+    out->e0 = c.e0;
+    out->normalizer = 1.0;
+    unsigned int det = 0, traj = 0;
+    CU(cudaMemcpy(&det, s->d_detcount, sizeof(det), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&traj, s->d_trajcount, sizeof(traj), cudaMemcpyDeviceToHost));
+    out->detectedtotal = det;
+    out->detectedcount = s->isdet ? std::min(det, c.maxdetphoton) : 0;   // overflow is a warning, data truncated (src/mmc_cu_host.cu:823-834)
+    out->trajcount = std::min(traj, c.maxjumpdebug);
+
+    if (out->detected && out->detectedcount) {
+        CU(cudaMemcpy(out->detected, s->d_detected, sizeof(float) * (size_t)out->detectedcount * s->cfg.reclen, cudaMemcpyDeviceToHost));
+    }
+
+    if (out->detseed && out->detectedcount && s->d_detseed) {
+        CU(cudaMemcpy(out->detseed, s->d_detseed, sizeof(uint64_t) * 2 * (size_t)out->detectedcount, cudaMemcpyDeviceToHost));
+    }
+
+    if (out->traj && out->trajcount && s->d_traj) {
+        CU(cudaMemcpy(out->traj, s->d_traj, sizeof(float) * MMCB_DEBUG_REC * (size_t)out->trajcount, cudaMemcpyDeviceToHost));
+    }
+
+    std::vector<double> dref;
+
+    if (c.issaveref && s->d_dref) {
+        dref.resize((size_t)m.nf * s->cfg.maxgate);
+        CU(cudaMemcpy(dref.data(), s->d_dref, sizeof(double) * dref.size(), cudaMemcpyDeviceToHost));
+    }
+
+    if (out->field) {
+        // raw sums -> double on the device (and elem->node spreading for nodal output), then one D2H copy
+        std::vector<double> W(s->fieldlen);
+        double* d_tmp = NULL;
+        const bool nodal = (!s->isgrid && c.basisorder);
+
+        if (nodal) {
+            CU(cudaMalloc(&d_tmp, sizeof(double) * s->fieldlen));
+            CU(cudaMemsetAsync(d_tmp, 0, sizeof(double) * s->fieldlen, s->stream));
+            CUK(mmcb_k_spread_nodes(s->d_field, d_tmp, s->d_elem, m.ne, m.nn, s->cfg.maxgate, c.srcnum, s->stream));
+            CU(cudaMemcpyAsync(W.data(), d_tmp, sizeof(double) * s->fieldlen, cudaMemcpyDeviceToHost, s->stream));
+        } else if (!s->acc_double) {
+            CU(cudaMalloc(&d_tmp, sizeof(double) * s->fieldlen));
+            CUK(mmcb_k_acc_to_double(s->d_field, d_tmp, s->fieldlen, s->stream));
+            CU(cudaMemcpyAsync(W.data(), d_tmp, sizeof(double) * s->fieldlen, cudaMemcpyDeviceToHost, s->stream));
+        } else {
+            CU(cudaMemcpyAsync(W.data(), s->d_field, sizeof(double) * s->fieldlen, cudaMemcpyDeviceToHost, s->stream));
+        }
+
+        CU(cudaStreamSynchronize(s->stream));
+
+        if (d_tmp) {
+            cudaFree(d_tmp);
+        }
+
+        if (c.isnormalized) {
+            double sum = 0;
+
+            for (int j = 0; j < c.srcnum; j++) {
+                double eabs = out->energytot[j] - out->energyesc[j];       // src/mmc_cu_host.cu:988
+                sum += normalize_field(s, W.data(), j == 0 && !dref.empty() ? dref.data() : NULL, (float)eabs, (float)out->energytot[j], j);
+            }
+
+            out->normalizer = sum / c.srcnum;
+        }
+
+        for (size_t i = 0; i < s->fieldlen; i++) {
+            out->field[i] += W[i];          // cfg->exportfield[i] += field[i]  (src/mmc_cu_host.cu:918-920)
+        }
+    }
+
+    if (out->dref && !dref.empty()) {
+        for (size_t i = 0; i < dref.size(); i++) {
+            out->dref[i] += dref[i];
+        }
+    }
+
+    return 0;
+}
+
+int mmcb_run_simulation(const mmcb_config* cfg, const mmcb_mesh* mesh, int device, mmcb_output* out) {
+    if (!out) {
+        return fail(MMCB_ERR_INPUT, "null output");
+    }
+
+    mmcb_session* s = mmcb_create(cfg, mesh, device);
+
+    if (!s) {
+        return g_code ? g_code : MMCB_ERR_CUDA;
+    }
+
+    int rc = 0;
+    float ms = 0.f;
+    const int respin = s->cfg.c.respin;
+    uint64_t per = s->cfg.c.nphoton / respin;
+
+    for (int it = 0; it < respin && rc == 0; it++) {         // src/mmc_cu_host.cu:656,893-906
+        uint64_t n = (it == respin - 1) ? s->cfg.c.nphoton - per * (respin - 1) : per;
+        rc = mmcb_launch(s, n, per * it, s->cfg.c.seed, it, NULL);
+
+        if (rc == 0) {
+            rc = mmcb_sync(s);
+        }
+
+        ms += s->last_ms;
+    }
+
+    if (rc == 0) {
+        rc = mmcb_fetch(s, NULL, NULL, out);
+        out->kernel_ms = ms;
+    }
+
+    std::string keep = g_err;
+    mmcb_destroy(s);
+    g_err = keep;
+    return rc;
+}
+
+}  // extern "C"

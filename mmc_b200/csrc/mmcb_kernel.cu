@@ -1,0 +1,1070 @@
+// mmc_b200 photon-transport kernels for sm_100a (hand-written; no CPU fallback exists).
+//
+// What the kernel computes is the reference's per-photon random walk (src/mmc_core.cl:1851-2161 with
+// mmc_raytrace.c semantics where the CUDA file has none); HOW it is computed is new:
+//   * one flattened, warp-converged state machine: every loop iteration is exactly one ray-tetrahedron
+//     step for every lane; a lane whose photon ends re-launches in place.  The reference runs
+//     `for photon: onephoton()` so a warp waits for its longest photon (src/mmc_core.cl:2190-2203).
+//   * one 96-byte record per tetrahedron fetched with three 256-bit gathers (see mmcb_types.h) instead of
+//     >=6 scattered loads from normal[], facenb[] and type[]; face flags make the Fresnel / void tests local.
+//   * fire-and-forget `red.global.add` deposits (double or float) -- the reference needs the returned old
+//     value for its MAX_ACCUM overflow trick (src/mmc_core.cl:904-912).
+//   * persistent warps claim photon ids in chunks from a global counter (work stealing); one xorshift128+
+//     stream per thread slot, bit-exact to src/mmc_core.cl:517-532.
+//   * detected-photon records are appended with warp-ballot compaction (one atomic per warp and iteration).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mmcb_types.h"
+
+#ifndef MMCB_ACC_T
+#define MMCB_ACC_T double
+#endif
+typedef MMCB_ACC_T acc_t;
+
+#define MMC_UNDEFINED   3.40282347e+38f
+#define EPS             1e-6f                  // src/mmc_mesh.h:70 (CUDA/CPU value)
+#define R_C0            3.335640951981520e-12f // src/mmc_core.cl:335
+#define R_MIN_MUS       1e9f
+#define FIX_PHOTON      1e-3f
+#define TWO_PI_D        (3.14159265358979323846 * 2.0)   // src/mmc_mesh.h:69: a double expression
+#define JUST_BELOW_ONE  0.9998f
+#define DELTA_MUA       1e-4f
+#define POOL_CHUNK      32
+
+__constant__ mmcb_kparam gp;
+__constant__ float4 gdet[MMCB_MAX_DET];
+
+// ----------------------------------------------------------------------------------------------------
+// RNG: xorshift128+, src/mmc_core.cl:517-561 (bit-exact)
+// ----------------------------------------------------------------------------------------------------
+struct Rng {
+    unsigned long long t0, t1;
+};
+__device__ __forceinline__ float rand01(Rng& r) {
+    unsigned long long s1 = r.t0;
+    const unsigned long long s0 = r.t1;
+    r.t0 = s0;
+    s1 ^= s1 << 23;
+    r.t1 = s1 ^ s0 ^ (s1 >> 18) ^ (s0 >> 5);
+    unsigned int lo = (unsigned int)(r.t1 + s0);
+    return __uint_as_float(0x3F800000U | (lo >> 9)) - 1.0f;
+}
+__device__ __forceinline__ float rand_scatlen(Rng& r) {
+    return -logf(rand01(r) + EPS);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// small helpers
+// ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld256(const void* p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ float sel4(const float* a, int j) {   // register-friendly a[j]
+    return j == 0 ? a[0] : (j == 1 ? a[1] : (j == 2 ? a[2] : a[3]));
+}
+__device__ __forceinline__ void red_add(acc_t* p, float v) {     // no return value => RED, not ATOM
+    atomicAdd(p, (acc_t)v);
+}
+
+struct Photon {
+    float px, py, pz;
+    float vx, vy, vz;
+    float w, t, slen, slen0;
+    int   eid;                 // 1-based current element
+    unsigned int oldidx;       // run-length merged deposit (src/mmc_core.cl:862,898-956)
+    float oldw;
+    unsigned int posidx;
+    unsigned int id;
+    int   fixcount;
+};
+
+// rotatevector, src/mmc_core.cl:1307-1330
+__device__ __forceinline__ void rotatevector(float& vx, float& vy, float& vz, float stheta, float ctheta, float sphi, float cphi) {
+    float px, py, pz;
+
+    if (vz > -1.f + EPS && vz < 1.f - EPS) {
+        float tmp0 = 1.f - vz * vz;
+        float tmp1 = stheta * rsqrtf(tmp0);
+        px = tmp1 * (vx * vz * cphi - vy * sphi) + vx * ctheta;
+        py = tmp1 * (vy * vz * cphi + vx * sphi) + vy * ctheta;
+        pz = -tmp1 * tmp0 * cphi + vz * ctheta;
+    } else {
+        px = stheta * cphi;
+        py = stheta * sphi;
+        pz = (vz > 0.f) ? ctheta : -ctheta;
+    }
+
+    float inv = rsqrtf(px * px + py * py + pz * pz);
+    vx = px * inv;
+    vy = py * inv;
+    vz = pz * inv;
+}
+
+// mc_next_scatter, src/mmc_core.cl:1344-1377
+__device__ __forceinline__ float next_scatter(float g, Photon& p, Rng& rng, float& mom) {
+    float nextslen = rand_scatlen(rng);
+    float tmp0 = (float)(TWO_PI_D * rand01(rng));
+    float sphi, cphi, stheta, ctheta;
+    sincosf(tmp0, &sphi, &cphi);
+
+    if (g > EPS) {
+        tmp0 = (1.f - g * g) / (1.f - g + 2.f * g * rand01(rng));
+        tmp0 *= tmp0;
+        tmp0 = (1.f + g * g - tmp0) / (2.f * g);
+        tmp0 = fmaxf(-1.f, fminf(tmp0, 1.f));
+        stheta = sqrtf(1.f - tmp0 * tmp0);
+        ctheta = tmp0;
+    } else {
+        float theta = acosf(2.f * rand01(rng) - 1.f);
+        sincosf(theta, &stheta, &ctheta);
+    }
+
+    rotatevector(p.vx, p.vy, p.vz, stheta, ctheta, sphi, cphi);
+    mom = 1.f - ctheta;
+    return nextslen;
+}
+
+// enclosing-element search for area sources: src/mmc_core.cl:1786-1827 (candidate list) preceded by a test of the
+// current element like the CPU path (src/mmc_raytrace.c:2599-2611)
+__device__ __noinline__ void find_launch_elem(Photon& p, const mmcb_kargs& a) {
+    const int outn[4][3] = {{0, 3, 1}, {3, 2, 1}, {0, 2, 3}, {0, 1, 2}};
+
+    for (int is = -1; is < gp.srcelemlen; is++) {
+        int cand = (is < 0) ? p.eid : a.srcelem[is];
+
+        if (cand <= 0) {
+            continue;
+        }
+
+        const int* ee = a.elem + 4 * (size_t)(cand - 1);
+        bool include = true;
+
+        for (int i = 0; i < 4; i++) {
+            const float* na = a.node + 3 * (size_t)(ee[outn[i][0]] - 1);
+            const float* nb = a.node + 3 * (size_t)(ee[outn[i][1]] - 1);
+            const float* nc = a.node + 3 * (size_t)(ee[outn[i][2]] - 1);
+            float abx = nb[0] - na[0], aby = nb[1] - na[1], abz = nb[2] - na[2];
+            float acx = nc[0] - na[0], acy = nc[1] - na[1], acz = nc[2] - na[2];
+            float sx = p.px - na[0], sy = p.py - na[1], sz = p.pz - na[2];
+            float nx = aby * acz - abz * acy, ny = abz * acx - abx * acz, nz = abx * acy - aby * acx;
+            float bary = -(sx * nx + sy * ny + sz * nz);
+
+            if (bary < -1e-4f) {
+                include = false;
+            }
+        }
+
+        if (include) {
+            p.eid = cand;
+            return;
+        }
+    }
+}
+
+// launchnewphoton, src/mmc_core.cl:1417-1834 (single-slot sources; multi-slot/adjoint srcdata is out of scope)
+template <bool GENERAL>
+__device__ __forceinline__ void launch_photon(Photon& p, Rng& rng, const mmcb_kargs& a) {
+    p.px = gp.srcpos[0];
+    p.py = gp.srcpos[1];
+    p.pz = gp.srcpos[2];
+    p.vx = gp.srcdir[0];
+    p.vy = gp.srcdir[1];
+    p.vz = gp.srcdir[2];
+    p.eid = gp.e0;
+    p.w = 1.f;
+    p.t = 0.f;
+    p.slen0 = 0.f;
+    p.oldidx = 0xFFFFFFFFu;
+    p.oldw = 0.f;
+    p.posidx = 0;
+    p.fixcount = 0;
+    p.slen = rand_scatlen(rng);
+    const int st = gp.srctype;
+
+    if (st == 0) {           // pencil :1521-1526
+        return;
+    }
+
+    float ox = p.px, oy = p.py, oz = p.pz;
+    bool canfocus = true;
+    const float* sp1 = gp.srcparam1;
+    const float* sp2 = gp.srcparam2;
+
+    if (st == 4 || st == 5 || st == 6) {        // planar / pattern / fourier :1531-1562
+        float rx = rand01(rng), ry = rand01(rng);
+        p.px = gp.srcpos[0] + rx * sp1[0] + ry * sp2[0];
+        p.py = gp.srcpos[1] + rx * sp1[1] + ry * sp2[1];
+        p.pz = gp.srcpos[2] + rx * sp1[2] + ry * sp2[2];
+        p.w = 1.f;
+
+        if (st == 5) {
+            int xsize = (int)sp1[3], ysize = (int)sp2[3];
+            p.posidx = min((int)(ry * JUST_BELOW_ONE * ysize), ysize - 1) * xsize + min((int)(rx * JUST_BELOW_ONE * xsize), xsize - 1);
+            p.w = (gp.srcnum > 1) ? 1.f : a.srcpattern[p.posidx];
+        } else if (st == 6) {
+            p.w = (cosf((floorf(sp1[3]) * rx + floorf(sp2[3]) * ry + sp1[3] - floorf(sp1[3])) * (float)TWO_PI_D) * (1.f - sp2[3] + floorf(sp2[3])) + 1.f) * 0.5f;
+        }
+
+        ox += (sp1[0] + sp2[0]) * 0.5f;
+        oy += (sp1[1] + sp2[1]) * 0.5f;
+        oz += (sp1[2] + sp2[2]) * 0.5f;
+    } else if (st == 9 || st == 10) {           // fourierx / fourierx2d :1566-1591
+        float rx = rand01(rng), ry = rand01(rng);
+        float tmp = sp1[3] * rsqrtf(sp1[0] * sp1[0] + sp1[1] * sp1[1] + sp1[2] * sp1[2]);
+        float v2x = tmp * (gp.srcdir[1] * sp1[2] - gp.srcdir[2] * sp1[1]);
+        float v2y = tmp * (gp.srcdir[2] * sp1[0] - gp.srcdir[0] * sp1[2]);
+        float v2z = tmp * (gp.srcdir[0] * sp1[1] - gp.srcdir[1] * sp1[0]);
+        p.px = gp.srcpos[0] + rx * sp1[0] + ry * v2x;
+        p.py = gp.srcpos[1] + rx * sp1[1] + ry * v2y;
+        p.pz = gp.srcpos[2] + rx * sp1[2] + ry * v2z;
+
+        if (st == 10) {
+            p.w = (sinf((sp2[0] * rx + sp2[2]) * (float)TWO_PI_D) * sinf((sp2[1] * ry + sp2[3]) * (float)TWO_PI_D) + 1.f) * 0.5f;
+        } else {
+            p.w = (cosf((sp2[0] * rx + sp2[1] * ry + sp2[2]) * (float)TWO_PI_D) * (1.f - sp2[3]) + 1.f) * 0.5f;
+        }
+
+        ox += (sp1[0] + v2x) * 0.5f;
+        oy += (sp1[1] + v2y) * 0.5f;
+        oz += (sp1[2] + v2z) * 0.5f;
+    } else if (st == 8 || st == 3) {            // disk / gaussian :1595-1636
+        float phi = (float)(TWO_PI_D * rand01(rng));
+        float sphi = sinf(phi), cphi = cosf(phi), r0;
+
+        if (st == 8) {
+            r0 = sqrtf(rand01(rng)) * sp1[0];
+        } else if (fabsf(gp.focus) < 1e-5f || fabsf(sp1[1]) < 1e-5f) {
+            r0 = sqrtf(-logf(rand01(rng))) * sp1[0];
+        } else {
+            float z0 = sp1[0] * sp1[0] * 3.14159265358979f / sp1[1];
+            r0 = sqrtf(-logf(rand01(rng)) * (1.f + (gp.focus * gp.focus / (z0 * z0)))) * sp1[0];
+        }
+
+        if (gp.srcdir[2] > -1.f + EPS && gp.srcdir[2] < 1.f - EPS) {
+            float tmp0 = 1.f - gp.srcdir[2] * gp.srcdir[2];
+            float tmp1 = r0 * rsqrtf(tmp0);
+            p.px = gp.srcpos[0] + tmp1 * (gp.srcdir[0] * gp.srcdir[2] * cphi - gp.srcdir[1] * sphi);
+            p.py = gp.srcpos[1] + tmp1 * (gp.srcdir[1] * gp.srcdir[2] * cphi + gp.srcdir[0] * sphi);
+            p.pz = gp.srcpos[2] - tmp1 * tmp0 * cphi;
+        } else {
+            p.px += r0 * cphi;
+            p.py += r0 * sphi;
+        }
+    } else if (st == 2 || st == 1 || st == 7) { // cone / isotropic / arcsine :1641-1684
+        float ang = (float)(TWO_PI_D * rand01(rng));
+        float sphi = sinf(ang), cphi = cosf(ang);
+
+        if (st == 2) {
+            do {
+                ang = (sp1[1] > 0) ? (float)(TWO_PI_D * rand01(rng)) : acosf(2.f * rand01(rng) - 1.f);
+            } while (ang > sp1[0]);
+        } else if (st == 1) {
+            ang = acosf(2.f * rand01(rng) - 1.f);
+        } else {
+            ang = 3.14159265358979f * rand01(rng);
+        }
+
+        float stheta = sinf(ang), ctheta = cosf(ang);
+        // direction relative to srcdir like the CPU path (src/mmc_raytrace.c:2479-2481); identical to
+        // src/mmc_core.cl:1676-1678 when srcdir=(0,0,1)
+        rotatevector(p.vx, p.vy, p.vz, stheta, ctheta, sphi, cphi);
+        canfocus = false;
+
+        if (p.eid > 0) {
+            return;
+        }
+    } else if (st == 11) {                      // zgaussian :1689-1701
+        float ang = (float)(TWO_PI_D * rand01(rng));
+        float sphi = sinf(ang), cphi = cosf(ang);
+        ang = sqrtf(-2.f * logf(rand01(rng))) * (1.f - 2.f * rand01(rng)) * sp1[0];
+        float stheta = sinf(ang), ctheta = cosf(ang);
+        rotatevector(p.vx, p.vy, p.vz, stheta, ctheta, sphi, cphi);
+        canfocus = false;
+    } else if (st == 12 || st == 13) {          // line / slit :1705-1735
+        float t = rand01(rng);
+        p.px += t * sp1[0];
+        p.py += t * sp1[1];
+        p.pz += t * sp1[2];
+
+        if (st == 12) {
+            float s, q;
+            t = 1.f - 2.f * rand01(rng);
+            s = 1.f - 2.f * rand01(rng);
+            q = sqrtf(1.f - p.vx * p.vx - p.vy * p.vy) * (rand01(rng) > 0.5f ? 1.f : -1.f);
+            float nx = p.vy * q - p.vz * s, ny = p.vz * t - p.vx * q, nz = p.vx * s - p.vy * t;
+            p.vx = nx;
+            p.vy = ny;
+            p.vz = nz;
+        }
+
+        ox += sp1[0] * 0.5f;
+        oy += sp1[1] * 0.5f;
+        oz += sp1[2] * 0.5f;
+        canfocus = (st == 13);
+    }
+
+    if (canfocus) {                             // :1742-1776
+        float f = gp.focus;
+
+        if (isnan(f)) {
+            float ang = (float)(TWO_PI_D * rand01(rng)), sphi, cphi, stheta, ctheta;
+            sincosf(ang, &sphi, &cphi);
+            ang = acosf(2.f * rand01(rng) - 1.f);
+            sincosf(ang, &stheta, &ctheta);
+            rotatevector(p.vx, p.vy, p.vz, stheta, ctheta, sphi, cphi);
+        } else if (f < 0.f && isinf(f)) {
+            float ang = (float)(TWO_PI_D * rand01(rng)), sphi, cphi;
+            sincosf(ang, &sphi, &cphi);
+            float stheta = sqrtf(rand01(rng));
+            float ctheta = sqrtf(1.f - stheta * stheta);
+            rotatevector(p.vx, p.vy, p.vz, stheta, ctheta, sphi, cphi);
+        } else if (f != 0.f) {
+            ox += f * p.vx;
+            oy += f * p.vy;
+            oz += f * p.vz;
+
+            if (f < 0.f) {
+                p.vx = p.px - ox;
+                p.vy = p.py - oy;
+                p.vz = p.pz - oz;
+            } else {
+                p.vx = ox - p.px;
+                p.vy = oy - p.py;
+                p.vz = oz - p.pz;
+            }
+
+            float rn = rsqrtf(p.vx * p.vx + p.vy * p.vy + p.vz * p.vz);
+            p.vx *= rn;
+            p.vy *= rn;
+            p.vz *= rn;
+        }
+    }
+
+    p.px += p.vx * EPS;                         // :1778
+    p.py += p.vy * EPS;
+    p.pz += p.vz * EPS;
+    find_launch_elem(p, a);
+}
+
+// Fresnel reflection / refraction, src/mmc_core.cl:1247-1303.  (nx,ny,nz): outward normal of the exit face.
+__device__ __forceinline__ void reflectray(Photon& p, int& neweid, float nx, float ny, float nz, float n1,
+        const float4* smed, const mmcb_kargs& a, Rng& rng) {
+    float Icos = fabsf(p.vx * nx + p.vy * ny + p.vz * nz);
+    float n2 = gp.nout;
+
+    if (neweid > 0) {
+        int t2 = a.tet[neweid - 1].type;         // rare path: one extra 4-byte gather
+        n2 = smed[t2].w;
+    }
+
+    float tmp0 = n1 * n1, tmp1 = n2 * n2;
+    float tmp2 = 1.f - tmp0 / tmp1 * (1.f - Icos * Icos);
+
+    if (tmp2 > 0.f && !(neweid <= 0 && gp.isreflect == 3)) {
+        float Re = tmp0 * Icos * Icos + tmp1 * tmp2;
+        tmp2 = sqrtf(tmp2);
+        float Im = 2.f * n1 * n2 * Icos * tmp2;
+        float Rtotal = (Re - Im) / (Re + Im);
+        Re = tmp1 * Icos * Icos + tmp0 * tmp2 * tmp2;
+        Rtotal = (Rtotal + (Re - Im) / (Re + Im)) * 0.5f;
+
+        if (rand01(rng) <= Rtotal) {
+            p.vx += -2.f * Icos * nx;
+            p.vy += -2.f * Icos * ny;
+            p.vz += -2.f * Icos * nz;
+            neweid = p.eid;
+        } else if (gp.isspecular == 2 && neweid == 0) {
+        } else {
+            float r = n1 / n2;
+            p.vx = tmp2 * nx + r * (p.vx - Icos * nx);
+            p.vy = tmp2 * ny + r * (p.vy - Icos * ny);
+            p.vz = tmp2 * nz + r * (p.vz - Icos * nz);
+        }
+    } else {
+        p.vx += -2.f * Icos * nx;
+        p.vy += -2.f * Icos * ny;
+        p.vz += -2.f * Icos * nz;
+        neweid = p.eid;
+    }
+
+    float inv = rsqrtf(p.vx * p.vx + p.vy * p.vy + p.vz * p.vz);
+    p.vx *= inv;
+    p.vy *= inv;
+    p.vz *= inv;
+}
+
+// deposit of a merged run (single source or photon-sharing patterns), src/mmc_core.cl:902-946
+template <bool GENERAL>
+__device__ __forceinline__ void flush_deposit(acc_t* field, unsigned int idx, float w, const Photon& p, const mmcb_kargs& a) {
+    if (!GENERAL || gp.srcnum == 1) {
+        red_add(field + idx, w);
+    } else {
+        for (int k = 0; k < gp.srcnum; k++) {
+            red_add(field + (size_t)idx * gp.srcnum + k, w * a.srcpattern[(size_t)p.posidx * gp.srcnum + k]);
+        }
+    }
+}
+
+__device__ __forceinline__ void savedebug(const Photon& p, const mmcb_kargs& a) {  // src/mmc_core.cl:692-704
+    unsigned int pos = atomicAdd(a.trajcount, 1u);
+
+    if (pos < gp.maxjumpdebug) {
+        float* d = a.traj + (size_t)pos * MMCB_DEBUG_REC;
+        d[0] = __uint_as_float(p.id);
+        d[1] = p.px;
+        d[2] = p.py;
+        d[3] = p.pz;
+        d[4] = p.w;
+        d[5] = __int_as_float(p.eid);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// the photon kernel.  GRID: dual-grid (DMMC) deposit instead of per-element; DET: detected-photon records;
+// GENERAL: area sources, photon sharing, replay, trajectories, diffuse reflectance.
+// ----------------------------------------------------------------------------------------------------
+template <bool GRID, bool DET, bool GENERAL>
+__global__ void __launch_bounds__(128)
+mmcb_photon_kernel(const mmcb_kargs a) {
+    extern __shared__ float4 smem4[];
+    float4* smed = smem4;                                   // media table, gp.nmedia entries
+    float* ppath = (float*)(smem4 + gp.nmedia);             // DET: [reclen][blockDim]
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xFFFFFFFFu;
+    acc_t* field = (acc_t*)a.field;
+
+    for (int i = threadIdx.x; i < gp.nmedia; i += blockDim.x) {
+        smed[i] = a.med[i];
+    }
+
+    __syncthreads();
+
+    Rng rng;
+    {
+        const uint32_t* s = a.seeds + 4 * (size_t)tid;   // xorshift128p_seed, src/mmc_core.cl:545-548
+        rng.t0 = ((unsigned long long)s[0] << 32) | s[1];
+        rng.t1 = ((unsigned long long)s[2] << 32) | s[3];
+    }
+    Rng initseed = rng;
+
+    Photon p;
+    p.eid = 0;
+    p.w = 0.f;
+    int state = 0;                    // 0: needs a photon, 1: in flight, 2: no photons left
+    float etot = 0.f, eesc = 0.f;     // per-thread tallies like src/mmc_core.cl:1908,2155
+    unsigned int nraytet = 0;
+    // warp-level photon pool (lane 0 owns it): ids [pool_next, pool_end)
+    unsigned long long pool_next = 0, pool_end = 0;
+    // static schedule: this thread's own range
+    unsigned long long my_next = 0, my_end = 0;
+
+    if (gp.schedule == 1) {
+        my_next = (unsigned long long)tid * gp.threadphoton + min(tid, gp.oddphotons);
+        my_end = my_next + gp.threadphoton + (tid < gp.oddphotons ? 1 : 0);
+    }
+
+    const int reclen = gp.reclen;
+    const int M = gp.maxmedia;
+#define PPATH(k) ppath[(k) * blockDim.x + threadIdx.x]
+
+    while (true) {
+        // ------------------------------------------------------------------ photon supply
+        unsigned need = __ballot_sync(FULL, state == 0);
+
+        if (need) {
+            unsigned long long myid = 0;
+            bool got = false;
+
+            if (gp.schedule == 1) {
+                if (state == 0 && my_next < my_end) {
+                    myid = my_next++;
+                    got = true;
+                }
+            } else {
+                int n = __popc(need);
+                unsigned long long base = 0;
+                int avail = 0;
+
+                if (lane == 0 && pool_end - pool_next < (unsigned long long)n) {
+                    // serve what is left of the old range first (base/avail), then open a fresh chunk
+                    base = pool_next;
+                    avail = (int)(pool_end - pool_next);
+                    unsigned long long want = (unsigned long long)(POOL_CHUNK + n - avail);
+                    unsigned long long g0 = atomicAdd(a.photon_counter, want);
+                    pool_next = min(g0, gp.nphoton);
+                    pool_end = max(min(g0 + want, gp.nphoton), pool_next);
+                }
+
+                // broadcast the pool and distribute: first `avail` needy lanes take the leftover range, the rest the pool
+                avail = __shfl_sync(FULL, avail, 0);
+                base = __shfl_sync(FULL, base, 0);
+                unsigned long long pn = __shfl_sync(FULL, pool_next, 0);
+                unsigned long long pe = __shfl_sync(FULL, pool_end, 0);
+                int rank = __popc(need & ((1u << lane) - 1));
+
+                if (state == 0) {
+                    if (rank < avail) {
+                        myid = base + rank;
+                        got = true;
+                    } else {
+                        unsigned long long cand = pn + (unsigned long long)(rank - avail);
+
+                        if (cand < pe) {
+                            myid = cand;
+                            got = true;
+                        }
+                    }
+                }
+
+                if (lane == 0) {
+                    unsigned long long used = (unsigned long long)max(0, n - avail);
+                    pool_next = min(pool_next + used, pool_end);
+                }
+            }
+
+            if (state == 0) {
+                if (got) {
+                    p.id = (unsigned int)(myid + gp.photon_offset);
+
+                    if (GENERAL && gp.isreplay) {           // src/mmc_core.cl:2191-2194
+                        rng.t0 = a.replayseed[2 * (size_t)p.id];
+                        rng.t1 = a.replayseed[2 * (size_t)p.id + 1];
+                    }
+
+                    if (DET) {
+                        initseed = rng;
+
+                        for (int k = 0; k < reclen; k++) {
+                            PPATH(k) = 0.f;
+                        }
+                    }
+
+                    launch_photon<GENERAL>(p, rng, a);
+
+                    if (DET) {
+                        if (!GENERAL || gp.srctype != 5 || gp.srcnum == 1) {
+                            PPATH(reclen - 1) = p.w;                       // :1894-1898
+                        } else {
+                            PPATH(reclen - 1) = __uint_as_float(p.posidx);
+                        }
+                    }
+
+                    if (!GENERAL || gp.srcnum == 1) {
+                        etot += p.w;
+                    } else {
+                        for (int k = 0; k < gp.srcnum; k++) {
+                            atomicAdd(a.energy + k, (double)(p.w * a.srcpattern[(size_t)p.posidx * gp.srcnum + k]));
+                        }
+                    }
+
+                    if (GENERAL && gp.savetraj) {
+                        savedebug(p, a);
+                    }
+
+                    state = 1;
+                } else {
+                    state = 2;
+                }
+            }
+        }
+
+        if (__all_sync(FULL, state == 2)) {
+            break;
+        }
+
+        int detid = 0;
+
+        if (state == 1) {
+        // ------------------------------------------------------------------ one ray-tetrahedron step
+        const mmcb_tetrec* rec = a.tet + (p.eid - 1);
+        float r0[8], r1[8], r2[8];
+        ld256(rec, r0);                                     // nx[4] ny[4]
+        ld256((const char*)rec + 32, r1);                   // nz[4] d[4]
+        ld256((const char*)rec + 64, r2);                   // nb[4] type flags
+        nraytet++;
+        float T[4];
+        #pragma unroll
+
+        for (int j = 0; j < 4; j++) {                       // src/mmc_core.cl:752-765
+            float S = p.vx * r0[j] + p.vy * r0[4 + j] + p.vz * r1[j];
+            float Tn = r1[4 + j] - (p.px * r0[j] + p.py * r0[4 + j] + p.pz * r1[j]);
+            T[j] = (S > 0.f) ? __fdividef(Tn, S) : 1e10f;
+        }
+
+        float Lmin = fminf(fminf(fminf(T[0], T[1]), T[2]), T[3]);
+        int faceidx = (Lmin == 1e10f) ? 4 : (Lmin == T[0] ? 0 : (Lmin == T[1] ? 1 : (Lmin == T[2] ? 2 : 3)));
+        const int type = __float_as_int(r2[4]);
+        const unsigned flags = __float_as_uint(r2[5]);
+        bool terminate = false, detect = false;
+        int exiteid = p.eid;          // value of r.eid at termination (<=0: left the mesh)
+
+        if (faceidx < 4 && Lmin >= 0.f) {
+            const float4 prop = smed[type];                 // mua mus g n
+            float Lmove = (prop.y <= EPS) ? R_MIN_MUS : __fdividef(p.slen, prop.y);
+            const bool isend = (Lmin > Lmove);
+            Lmove = isend ? Lmove : Lmin;
+            const float rc = prop.w * R_C0;
+            bool timeup = false;
+
+            if ((int)((p.t + Lmove * rc - gp.tstart) * gp.Rtstep) > gp.maxgate - 1) {   // :803-807
+                timeup = true;
+                Lmove = (gp.tend - p.t) / rc - 1e-4f;
+            }
+
+            float currweight = p.w;
+            float totalloss = __expf(-prop.x * Lmove);
+            p.w *= totalloss;
+            totalloss = 1.f - totalloss;
+
+            if (GENERAL && gp.isreplay) {                   // :814-829
+                if (gp.outputtype == 4 || gp.outputtype == 3) {
+                    currweight = Lmove * a.replayweight[p.id] + p.w;
+                } else if (gp.outputtype == 5) {
+                    currweight = ((p.slen0 < EPS) ? 1.f : (Lmove * prop.y / p.slen0)) * a.replayweight[p.id] + p.w;
+                }
+            }
+
+            p.slen -= Lmove * prop.y;
+            float ww = currweight - p.w;
+            p.t += Lmove * rc;
+            int gate;
+
+            if (GENERAL && (gp.outputtype == 4 || gp.outputtype == 5)) {
+                gate = min((int)(a.replaytime[p.id] * gp.Rtstep), gp.maxgate - 1);
+            } else {
+                gate = min((int)((p.t - gp.tstart) * gp.Rtstep), gp.maxgate - 1);
+            }
+
+            const unsigned int tshift = (unsigned int)gate * gp.framelen;
+
+            if (gp.outputtype != 2 && gp.outputtype != 4 && gp.outputtype != 5) {       // :844-851
+                ww = (prop.x < EPS) ? (currweight * Lmove) : __fdividef(ww, prop.x);
+            }
+
+            const bool flushnow = timeup || !isend;
+
+            if (!GRID) {                                    // :856-1010
+                unsigned int newidx = (unsigned int)(p.eid - 1) + tshift;
+
+                if (p.oldidx == 0xFFFFFFFFu) {
+                    p.oldidx = newidx;
+                }
+
+                if (newidx != p.oldidx) {
+                    if (p.oldw > 0.f) {
+                        flush_deposit<GENERAL>(field, p.oldidx, p.oldw, p, a);
+                    }
+
+                    p.oldidx = newidx;
+                    p.oldw = ww;
+                } else {
+                    p.oldw += ww;
+                }
+
+                if (flushnow) {
+                    flush_deposit<GENERAL>(field, newidx, p.oldw, p, a);
+                    p.oldw = 0.f;
+                }
+            } else {                                        // dual-grid deposit :1022-1206
+                int seg = ((int)(Lmove * gp.dstep) + 1) << 1;
+                float seglen = Lmove / seg;
+                float segdecay = __expf(-prop.x * seglen);
+                float dx = p.vx * seglen, dy = p.vy * seglen, dz = p.vz * seglen;
+                float sx = (p.px - gp.nmin[0]) + dx * 0.5f, sy = (p.py - gp.nmin[1]) + dy * 0.5f, sz = (p.pz - gp.nmin[2]) + dz * 0.5f;
+                float frac = (totalloss == 0.f) ? 0.f : (1.f - segdecay) / totalloss;
+                float segw = ww;
+
+                for (int k = 0; k < seg; k++) {
+                    int ix = (sx > 0.f) ? __float2int_rd(sx * gp.dstep) : 0;
+                    int iy = (sy > 0.f) ? __float2int_rd(sy * gp.dstep) : 0;
+                    int iz = (sz > 0.f) ? __float2int_rd(sz * gp.dstep) : 0;
+                    unsigned int newidx = (unsigned int)(iz * gp.crop0[1] + iy * gp.crop0[0] + ix) + tshift;
+
+                    if (p.oldidx == 0xFFFFFFFFu) {
+                        p.oldidx = newidx;
+                    }
+
+                    float dep = segw * frac;
+
+                    if (newidx != p.oldidx) {
+                        flush_deposit<GENERAL>(field, p.oldidx, p.oldw, p, a);
+                        p.oldidx = newidx;
+                        p.oldw = dep;
+                    } else {
+                        p.oldw += dep;
+                    }
+
+                    if (flushnow) {
+                        flush_deposit<GENERAL>(field, newidx, p.oldw, p, a);
+                        p.oldw = 0.f;
+                    }
+
+                    segw *= segdecay;
+                    sx += dx;
+                    sy += dy;
+                    sz += dz;
+                }
+            }
+
+            p.px += Lmove * p.vx;                           // :1222
+            p.py += Lmove * p.vy;
+            p.pz += Lmove * p.vz;
+            // progress guard (not in the reference): a photon that makes no headway for MMCB_MAX_STALL consecutive steps is
+            // trapped between degenerate/inverted tetrahedra (the reference CPU path spins forever there) and is dropped
+            p.fixcount = (Lmove > 0.f) ? 0 : (p.fixcount + 0x100);
+
+            if (DET && Lmove > 0.f && type > 0 && type <= M) {           // :1943-1945
+                PPATH(M + type - 1) += Lmove;
+            }
+
+            if (timeup || p.fixcount >= (MMCB_MAX_STALL << 8)) {
+                terminate = true;                           // :1928-1930 / :2007-2009 (photon stays inside: no detection)
+            } else if (!isend) {
+                // ---- cross the face: neighbour hop + boundary physics :1950-1990
+                // r.p0 = r.pout: already there, Lmove == Lmin on this branch
+                int neweid = __float_as_int(sel4(r2, faceidx));
+
+                if (gp.isreflect && (flags & MMCB_F_REFLECT(faceidx))) {
+                    reflectray(p, neweid, sel4(r0, faceidx), sel4(r0 + 4, faceidx), sel4(r1, faceidx), prop.w, smed, a, rng);
+                }
+
+                if (neweid <= 0) {
+                    terminate = true;
+                    detect = true;
+                    exiteid = neweid;
+                } else if (neweid != p.eid) {
+                    if ((flags & MMCB_F_FROM_VOID(faceidx)) && !gp.voidtime) {
+                        p.t = 0.f;                          // :1970-1978
+                    }
+
+                    if ((flags & MMCB_F_TO_VOID(faceidx)) && !gp.isextdet) {
+                        terminate = true;                   // :1981-1990 (r.eid = 0)
+                        detect = true;
+                        exiteid = 0;
+                    } else {
+                        p.eid = neweid;
+                    }
+                }
+            } else {
+                // ---- end of the scattering path: roulette :2101-2114, then a new direction :2117-2135
+                bool dead = false;
+
+                if (gp.doroulette && gp.minenergy > 0.f && p.w < gp.minenergy) {
+                    if (rand01(rng) * gp.roulettesize <= 1.f) {
+                        p.w *= gp.roulettesize;
+                    } else {
+                        dead = true;
+                    }
+                }
+
+                if (dead) {
+                    terminate = true;
+                } else {
+                    float mom;
+                    p.slen0 = next_scatter(prop.z, p, rng, mom);
+                    p.slen = p.slen0;
+
+                    if (GENERAL && gp.savetraj) {
+                        savedebug(p, a);
+                    }
+
+                    if (DET && type > 0 && type <= M) {
+                        if (gp.ismomentum) {
+                            PPATH(2 * M + type - 1) += mom;
+                        }
+
+                        PPATH(type - 1) += 1.f;
+                    }
+                }
+            }
+        } else {
+            // no exit face found: pull the photon towards the centroid and retry (:1932-1935, :2013-2024)
+            if ((p.fixcount++ & 0xFF) < MMCB_MAX_TRIAL) {
+                float4 c = a.cent[p.eid - 1];
+                p.px += (c.x - p.px) * FIX_PHOTON;
+                p.py += (c.y - p.py) * FIX_PHOTON;
+                p.pz += (c.z - p.pz) * FIX_PHOTON;
+            } else {
+                terminate = true;                           // r.eid = ID_UNDEFINED: dropped without detection
+            }
+        }
+
+        // ------------------------------------------------------------------ photon end: tallies + detection
+        if (terminate) {
+            if (detect) {
+                if (GENERAL && gp.issaveref && exiteid < 0 && a.dref) {     // src/mmc_raytrace.c:2000-2003
+                    int g = min((int)((p.t - gp.tstart) * gp.Rtstep), gp.maxgate - 1);
+                    atomicAdd(a.dref + ((size_t)g * gp.nf + (-exiteid - 1)), (double)p.w);
+                }
+
+                if (DET) {                                  // finddetector :608-621 / wide-field :2072
+                    if (gp.isextdet && type == M + 1) {
+                        detid = p.eid;
+                    } else {
+                        for (int i = 0; i < gp.detnum; i++) {
+                            float4 dp = gdet[i];
+                            float ddx = dp.x - p.px, ddy = dp.y - p.py, ddz = dp.z - p.pz;
+
+                            if (ddx * ddx + ddy * ddy + ddz * ddz < dp.w * dp.w) {
+                                detid = i + 1;
+                                break;
+                            }
+                        }
+                    }
+                }
+            }
+
+            if (GENERAL && gp.savetraj) {
+                savedebug(p, a);
+            }
+
+            if (!GENERAL || gp.srcnum == 1) {
+                eesc += p.w;
+            } else {
+                for (int k = 0; k < gp.srcnum; k++) {
+                    atomicAdd(a.energy + MMCB_MAX_SRCNUM + k, (double)(p.w * a.srcpattern[(size_t)p.posidx * gp.srcnum + k]));
+                }
+            }
+
+            // a merged deposit may still be pending (photon died at a scattering site): the reference drops it only
+            // when the run ended on `isend` -- it flushes on the NEXT step, which never comes; we keep that behaviour.
+            state = 0;
+        }
+        }   // state == 1
+
+        if (DET) {
+            unsigned detmask = __ballot_sync(FULL, detid != 0);
+
+            if (detmask) {                                  // warp-ballot compaction of savedetphoton (:624-682)
+                unsigned int base = 0;
+
+                if (lane == __ffs(detmask) - 1) {
+                    base = atomicAdd(a.detcount, (unsigned int)__popc(detmask));
+                }
+
+                base = __shfl_sync(FULL, base, __ffs(detmask) - 1);
+
+                if (detid) {
+                    unsigned int slot = base + __popc(detmask & ((1u << lane) - 1));
+
+                    if (slot < gp.maxdetphoton) {
+                        float* out = a.detected + (size_t)slot * (reclen + 1);
+
+                        if (gp.issaveexit) {
+                            PPATH(reclen - 7) = p.px;
+                            PPATH(reclen - 6) = p.py;
+                            PPATH(reclen - 5) = p.pz;
+                            PPATH(reclen - 4) = p.vx;
+                            PPATH(reclen - 3) = p.vy;
+                            PPATH(reclen - 2) = p.vz;
+                        }
+
+                        out[0] = (float)detid;
+
+                        for (int k = 0; k < reclen; k++) {
+                            out[1 + k] = PPATH(k);
+                        }
+
+                        if (gp.issaveseed) {
+                            a.detseed[2 * (size_t)slot] = initseed.t0;
+                            a.detseed[2 * (size_t)slot + 1] = initseed.t1;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+#undef PPATH
+    // ---------------------------------------------------------------------- per-warp reduction of the tallies
+    double dt = etot, de = eesc, dr = (double)nraytet;
+    #pragma unroll
+
+    for (int o = 16; o > 0; o >>= 1) {
+        dt += __shfl_xor_sync(FULL, dt, o);
+        de += __shfl_xor_sync(FULL, de, o);
+        dr += __shfl_xor_sync(FULL, dr, o);
+    }
+
+    if (lane == 0) {
+        if (!GENERAL || gp.srcnum == 1) {
+            atomicAdd(a.energy, dt);
+            atomicAdd(a.energy + MMCB_MAX_SRCNUM, de);
+        }
+
+        atomicAdd(a.raytet, dr);
+    }
+}
+
+// elem -> node spreading for nodal output with the BLB tracer (the reference does this on the host,
+// src/mmc_cu_host.cu:929-975): node += 0.25 * elem for the 4 nodes of each element, per gate and pattern.
+__global__ void mmcb_spread_nodes_kernel(const acc_t* __restrict__ efield, double* __restrict__ nfield, const int* __restrict__ elem,
+        int ne, int nn, int maxgate, int srcnum) {
+    size_t total = (size_t)ne * maxgate * srcnum;
+
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int s = (int)(i % srcnum);
+        size_t r = i / srcnum;
+        int e = (int)(r % ne);
+        int g = (int)(r / ne);
+        double w = (double)efield[i] * 0.25;
+
+        if (w != 0.0) {
+            const int* ee = elem + 4 * (size_t)e;
+            #pragma unroll
+
+            for (int k = 0; k < 4; k++) {
+                atomicAdd(nfield + ((size_t)g * nn + (ee[k] - 1)) * srcnum + s, w);
+            }
+        }
+    }
+}
+
+__global__ void mmcb_acc_to_double_kernel(const acc_t* __restrict__ in, double* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        out[i] = (double)in[i];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// host-callable launchers (called from mmcb_host.cu)
+// ----------------------------------------------------------------------------------------------------
+extern "C" int mmcb_k_upload_param(const mmcb_kparam* hp, const float* det4, int detnum, cudaStream_t st) {
+    cudaError_t e = cudaMemcpyToSymbolAsync(gp, hp, sizeof(mmcb_kparam), 0, cudaMemcpyHostToDevice, st);
+
+    if (e == cudaSuccess && detnum > 0) {
+        e = cudaMemcpyToSymbolAsync(gdet, det4, sizeof(float4) * detnum, 0, cudaMemcpyHostToDevice, st);
+    }
+
+    return (int)e;
+}
+
+template <bool GRID, bool DET, bool GENERAL>
+static int launch_variant(const mmcb_kargs& a, int grid, int block, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(mmcb_photon_kernel<GRID, DET, GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+
+    if (e != cudaSuccess) {
+        return (int)e;
+    }
+
+    mmcb_photon_kernel<GRID, DET, GENERAL><<<grid, block, smem, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int isgrid, int isdet, int isgeneral, cudaStream_t st) {
+    int v = (isgrid ? 4 : 0) | (isdet ? 2 : 0) | (isgeneral ? 1 : 0);
+
+    switch (v) {
+        case 0:
+            return launch_variant<false, false, false>(*a, grid, block, smem, st);
+
+        case 1:
+            return launch_variant<false, false, true>(*a, grid, block, smem, st);
+
+        case 2:
+            return launch_variant<false, true, false>(*a, grid, block, smem, st);
+
+        case 3:
+            return launch_variant<false, true, true>(*a, grid, block, smem, st);
+
+        case 4:
+            return launch_variant<true, false, false>(*a, grid, block, smem, st);
+
+        case 5:
+            return launch_variant<true, false, true>(*a, grid, block, smem, st);
+
+        case 6:
+            return launch_variant<true, true, false>(*a, grid, block, smem, st);
+
+        default:
+            return launch_variant<true, true, true>(*a, grid, block, smem, st);
+    }
+}
+
+extern "C" int mmcb_k_occupancy(int block, size_t smem, int isgrid, int isdet, int isgeneral, int* blocks_per_sm) {
+    int v = (isgrid ? 4 : 0) | (isdet ? 2 : 0) | (isgeneral ? 1 : 0);
+    cudaError_t e;
+#define OCC(G, D, N) e = cudaFuncSetAttribute(mmcb_photon_kernel<G, D, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, mmcb_photon_kernel<G, D, N>, block, smem)
+
+    switch (v) {
+        case 0:
+            OCC(false, false, false);
+            break;
+
+        case 1:
+            OCC(false, false, true);
+            break;
+
+        case 2:
+            OCC(false, true, false);
+            break;
+
+        case 3:
+            OCC(false, true, true);
+            break;
+
+        case 4:
+            OCC(true, false, false);
+            break;
+
+        case 5:
+            OCC(true, false, true);
+            break;
+
+        case 6:
+            OCC(true, true, false);
+            break;
+
+        default:
+            OCC(true, true, true);
+            break;
+    }
+
+#undef OCC
+    return (int)e;
+}
+
+extern "C" int mmcb_k_spread_nodes(const void* efield, double* nfield, const int* elem, int ne, int nn, int maxgate, int srcnum, cudaStream_t st) {
+    mmcb_spread_nodes_kernel<<<148 * 8, 256, 0, st>>>((const acc_t*)efield, nfield, elem, ne, nn, maxgate, srcnum);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int mmcb_k_acc_to_double(const void* in, double* out, size_t n, cudaStream_t st) {
+    mmcb_acc_to_double_kernel<<<148 * 8, 256, 0, st>>>((const acc_t*)in, out, n);
+    return (int)cudaGetLastError();
+}
+
+// RNG known-answer kernel: stream i draws `ndraw` floats with the same rand01() the photon kernel uses
+__global__ void mmcb_rng_kernel(const uint32_t* __restrict__ seeds, int nstream, int ndraw, float* __restrict__ out,
+                                unsigned long long* __restrict__ state_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+
+    if (i >= nstream) {
+        return;
+    }
+
+    Rng r;
+    r.t0 = ((unsigned long long)seeds[4 * i] << 32) | seeds[4 * i + 1];
+    r.t1 = ((unsigned long long)seeds[4 * i + 2] << 32) | seeds[4 * i + 3];
+
+    for (int k = 0; k < ndraw; k++) {
+        out[(size_t)i * ndraw + k] = rand01(r);
+    }
+
+    state_out[2 * i] = r.t0;
+    state_out[2 * i + 1] = r.t1;
+}
+
+extern "C" int mmcb_k_rng(const uint32_t* dseeds, int nstream, int ndraw, float* dout, unsigned long long* dstate, cudaStream_t st) {
+    mmcb_rng_kernel<<<(nstream + 127) / 128, 128, 0, st>>>(dseeds, nstream, ndraw, dout, dstate);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int mmcb_k_acc_is_double(void) {
+    return sizeof(acc_t) == 8;
+}

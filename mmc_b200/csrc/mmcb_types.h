@@ -1,0 +1,92 @@
+// Shared host/device plain-data types of the mmc_b200 engine.
+#pragma once
+#include <stdint.h>
+
+#define MMCB_MAX_DET      256       // point detectors kept in constant memory
+#define MMCB_MAX_SRCNUM   16        // patterns simulated together (photon sharing)
+#define MMCB_MAX_TRIAL    3         // src/mmc_core.cl:355
+#define MMCB_MAX_STALL    1000      // consecutive zero-length steps before a trapped photon is dropped
+#define MMCB_DEBUG_REC    6         // floats per trajectory record (src/mmc_core.cl:360)
+
+// One tetrahedron = one 96-byte record, 32-byte aligned: three 256-bit gathers (LDG.E.256) bring everything a
+// branch-less Badouel step needs -- the reference reads the same data from three arrays (normal[4*eid..],
+// facenb[eid], type[eid]; src/mmc_core.cl:747-754,1954,1924) with six or more scattered load instructions.
+//   sector 0: nx[4] ny[4]     sector 1: nz[4] d[4]     sector 2: nb[4] type flags pad pad
+// Faces are in tracer order j=0..3 (nodes out[j], src/mmc_mesh.c:59); nb[] is ALREADY permuted by faceorder[]
+// (src/mmc_mesh.c:84) so nb[j] is the element behind tracer face j; exterior faces hold -(1..nf)
+// (src/mmc_mesh.c:1466-1474).
+struct __attribute__((aligned(32))) mmcb_tetrec {
+    float nx[4], ny[4], nz[4], d[4];
+    int   nb[4];
+    int   type;
+    unsigned int flags;
+    int   pad[2];
+};
+// flags bits (pre-computed per session from the media table, nout and the boundary condition)
+#define MMCB_F_REFLECT(j)  (1u << (j))        // crossing face j calls reflectray (src/mmc_core.cl:1957-1958)
+#define MMCB_F_TO_VOID(j)  (1u << (4 + (j)))  // this tet has type>0, the neighbour has type 0 (src/mmc_core.cl:1981)
+#define MMCB_F_FROM_VOID(j) (1u << (8 + (j))) // this tet has type 0, the neighbour type>0 (src/mmc_core.cl:1970)
+
+// Havel / Plucker tetrahedron record (256 bytes): the per-face / per-edge tables of tracer_build
+// (src/mmc_mesh.c:1518-1567) followed by neighbours, node ids, type and flags.
+struct __attribute__((aligned(32))) mmcb_tetrec_big {
+    float tab[48];        // Havel: 4 faces x {n̂(4), e1(4), e2(4)}; Plucker: d[6][4] then m[6][4]
+    int   nb[4];          // facenb permuted to tracer face order
+    int   node[4];        // element node ids (1-based)
+    int   type;
+    unsigned int flags;
+    int   pad[6];
+};
+
+struct mmcb_kparam {
+    // source
+    float srcpos[4], srcdir[4], srcparam1[4], srcparam2[4];
+    int   srctype, srcnum, srcelemlen, e0;
+    float focus;
+    // time gates
+    float tstart, tend, Rtstep;
+    int   maxgate;
+    // physics switches
+    int   isreflect, isspecular, voidtime, isextdet, outputtype, method, basisorder;
+    float minenergy, roulettesize, nout;
+    int   doroulette;            // (tend-tstart)*Rtstep <= 1 (src/mmc_core.cl:2101)
+    // mesh sizes
+    int   nn, ne, nf, maxmedia;
+    unsigned int framelen;       // per-gate stride of the accumulator volume
+    // dual grid
+    float nmin[3]; float dstep;  // dstep = 1/steps.x
+    unsigned int crop0[3];
+    // detection
+    int   issavedet, ismomentum, issaveexit, issaveseed, issaveref, detnum, reclen;
+    unsigned int maxdetphoton;
+    // replay / debug
+    int   isreplay, savetraj;
+    unsigned int maxjumpdebug;
+    // scheduling
+    int   schedule;
+    unsigned long long nphoton, photon_offset;
+    int   threadphoton, oddphotons;
+    int   nmedia;                // entries of the media table (prop+1+isextdet)
+};
+
+struct mmcb_kargs {
+    const mmcb_tetrec* tet;
+    const mmcb_tetrec_big* tetbig;
+    const float4* cent;          // element centroids (fixphoton, src/mmc_core.cl:1390-1402)
+    const float*  node;          // nn*3
+    const int*    elem;          // ne*4
+    const int*    srcelem;
+    const float4* med;           // media table (copied to shared memory by each CTA)
+    const float*  srcpattern;
+    const uint32_t* seeds;       // nthread*4
+    const unsigned long long* replayseed;
+    const float* replayweight;
+    const float* replaytime;
+    void*   field;               // accumulator volume
+    double* dref;
+    float*  detected; unsigned int* detcount; unsigned long long* detseed;
+    float*  traj;     unsigned int* trajcount;
+    double* energy;              // tot[16], esc[16]
+    double* raytet;
+    unsigned long long* photon_counter;
+};

@@ -58,7 +58,7 @@ def tet_volume6(node, elem):
     (mesh_getvolume, src/mmc_mesh.c:920-937 flips nodes 3,4 when this is negative)."""
     p = node.astype(np.float64)[elem - 1]
     a, b, c = p[:, 1] - p[:, 0], p[:, 2] - p[:, 0], p[:, 3] - p[:, 0]
-    return np.einsum("ij,ij->i", np.cross(a, b), c)
+    return -np.einsum("ij,ij->i", np.cross(a, b), c)
 
 
 def reorient(node, elem):

@@ -246,7 +246,8 @@ static void mesh_srcdetelem(orc_mesh* m) {
 }
 
 orc_mesh* orc_mesh_create(int nn, const float* node, int ne, const int* elem, const int* type,
-                          int prop, const float* med, float nout, float unitinmm, const int* facenb_or_null) {
+                          int prop, const float* med, float nout, float unitinmm, const int* facenb_or_null,
+                          const float* evol_or_null) {
     int i;
     orc_mesh* m = (orc_mesh*)calloc(1, sizeof(orc_mesh));
     m->nn = nn;
@@ -282,7 +283,24 @@ orc_mesh* orc_mesh_create(int nn, const float* node, int ne, const int* elem, co
             m->med[4 * i] *= unitinmm;
         }
 
-    mesh_getvolume(m);
+    if (evol_or_null) {   /* mesh_loadelemvol src/mmc_mesh.c:723-761: file volumes => no orientation swap */
+        int j;
+        m->evol = (float*)malloc(sizeof(float) * ne);
+        memcpy(m->evol, evol_or_null, sizeof(float) * ne);
+        m->nvol = (float*)calloc(nn, sizeof(float));
+
+        for (i = 0; i < ne; i++) {
+            if (m->type[i] == 0) {
+                continue;
+            }
+
+            for (j = 0; j < 4; j++) {
+                m->nvol[m->elem[4 * i + j] - 1] += m->evol[i] * 0.25f;
+            }
+        }
+    } else {
+        mesh_getvolume(m);
+    }
 
     if (facenb_or_null) {
         m->facenb = (int*)malloc(sizeof(int) * 4 * ne);

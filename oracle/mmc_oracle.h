@@ -98,7 +98,8 @@ typedef struct orc_result {
 } orc_result;
 
 orc_mesh* orc_mesh_create(int nn, const float* node, int ne, const int* elem, const int* type,
-                          int prop, const float* med, float nout, float unitinmm, const int* facenb_or_null);
+                          int prop, const float* med, float nout, float unitinmm, const int* facenb_or_null,
+                          const float* evol_or_null);
 void orc_mesh_free(orc_mesh* m);
 void orc_mesh_build_tracer(orc_mesh* m, int method);
 int  orc_mesh_initelem(const orc_mesh* m, const float* srcpos, float* bary4);

@@ -77,7 +77,7 @@ def lib():
         L = C.CDLL(LIB)
         L.orc_mesh_create.restype = C.POINTER(Mesh)
         L.orc_mesh_create.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
-                                      C.c_float, C.c_float, C.c_void_p]
+                                      C.c_float, C.c_float, C.c_void_p, C.c_void_p]
         L.orc_mesh_free.argtypes = [C.POINTER(Mesh)]
         L.orc_mesh_build_tracer.argtypes = [C.POINTER(Mesh), C.c_int]
         L.orc_run.argtypes = [C.POINTER(Mesh), C.POINTER(Config), C.POINTER(Result)]
@@ -127,7 +127,7 @@ def _f4(v):
     return (C.c_float * 4)(*[float(x) for x in v[:4]])
 
 
-def run(node, elem, etype, med, facenb=None, **kw):
+def run(node, elem, etype, med, facenb=None, evol=None, **kw):
     """Run the oracle.  med: [(mua,mus,g,n)] for media 1..prop (medium 0 is added like mesh_loadmedia).
     Returns a dict with field [maxgate, datalen, srcnum] (float64) and tallies."""
     L = lib()
@@ -143,9 +143,10 @@ def run(node, elem, etype, med, facenb=None, **kw):
     prop = len(med)
     medfull = np.ascontiguousarray(np.vstack([[0, 0, 1, p["nout"]], med]), dtype=np.float32)
     fnb = None if facenb is None else np.ascontiguousarray(facenb, dtype=np.int32)
+    ev = None if evol is None else np.ascontiguousarray(evol, dtype=np.float32)
     mesh = L.orc_mesh_create(len(node), node.ctypes.data, len(elem), elem.ctypes.data, etype.ctypes.data, prop,
                              medfull.ctypes.data, C.c_float(p["nout"]), C.c_float(p["unitinmm"]),
-                             None if fnb is None else fnb.ctypes.data)
+                             None if fnb is None else fnb.ctypes.data, None if ev is None else ev.ctypes.data)
     try:
         cfg = Config()
         keep = []
@@ -230,7 +231,7 @@ def ref_available(cuda=False):
     return os.path.exists(REF_CUDA_BIN if cuda else REF_BIN)
 
 
-def write_mesh_files(dirname, tag, node, elem, etype, med):
+def write_mesh_files(dirname, tag, node, elem, etype, med, evol=None):
     """node_/elem_/prop_ text files (formats: SURVEY.md Appendix D; src/mmc_mesh.c:455-550,668-713)."""
     node = np.asarray(node)
     elem = np.asarray(elem)
@@ -242,6 +243,11 @@ def write_mesh_files(dirname, tag, node, elem, etype, med):
         f.write("1 %d\n" % len(elem))
         rows = np.column_stack([np.arange(1, len(elem) + 1), elem, etype])
         np.savetxt(f, rows, fmt="%d")
+    if evol is not None:   # velem_<id>.dat: given volumes => the loader does not re-orient elements (src/mmc_mesh.c:723-761)
+        with open(os.path.join(dirname, "velem_%s.dat" % tag), "w") as f:
+            f.write("1 %d\n" % len(elem))
+            for i, v in enumerate(np.asarray(evol, dtype=np.float64)):
+                f.write("%d %.9e\n" % (i + 1, v))
     med = np.asarray(med, dtype=np.float64).reshape(-1, 4)
     with open(os.path.join(dirname, "prop_%s.dat" % tag), "w") as f:
         f.write("1 %d\n" % len(med))
@@ -249,7 +255,7 @@ def write_mesh_files(dirname, tag, node, elem, etype, med):
             f.write("%d %.9g %.9g %.9g %.9g\n" % (i + 1, m[0], m[1], m[2], m[3]))
 
 
-def run_ref(node, elem, etype, med, *, nthread=1, cuda=False, extra_args=(), timeout=3600, keep_dir=None, **kw):
+def run_ref(node, elem, etype, med, *, nthread=1, cuda=False, extra_args=(), timeout=3600, keep_dir=None, evol=None, **kw):
     """Run oracle/_ref/mmc_ref (or mmc_refcuda) on the same inputs; returns dict(field, absorbed_frac, speed, ...)."""
     p = dict(DEFAULTS)
     p.update(kw)
@@ -257,7 +263,7 @@ def run_ref(node, elem, etype, med, *, nthread=1, cuda=False, extra_args=(), tim
     tmp = keep_dir or tempfile.mkdtemp(prefix="mmcref_")
     os.makedirs(tmp, exist_ok=True)
     tag = "t"
-    write_mesh_files(tmp, tag, node, elem, etype, med)
+    write_mesh_files(tmp, tag, node, elem, etype, med, evol)
     det = np.zeros((0, 4)) if p["detpos"] is None else np.asarray(p["detpos"], dtype=np.float64).reshape(-1, 4)
     with open(os.path.join(tmp, "in.inp"), "w") as f:
         f.write("%d\n%d\n" % (p["nphoton"], p["seed"]))

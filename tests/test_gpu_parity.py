@@ -1,0 +1,174 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every test goes through the C-ABI library
+(mmc_b200/libmmc_b200.so) via the ctypes host layer; the CPU oracle (oracle/) is only the checker.
+
+Tolerances (north_star): RNG bit-exact; absorbed/escaped energy fractions within 0.1 % at >=1e8 photons --
+here, at 2e5..1e6 photons, within 4 sigma of the Monte Carlo noise (stated per test); fluence compared where
+it exceeds a fraction of the maximum."""
+import numpy as np
+import pytest
+
+import cases
+import orc
+
+pytestmark = pytest.mark.gpu
+
+mmc = pytest.importorskip("mmc_b200")
+
+
+def _cfg(node, elem, et, med, **kw):
+    names = {cases.PLUCKER: "plucker", cases.HAVEL: "havel", cases.BLBADOUEL: "elem", cases.GRID: "grid"}
+    c = dict(node=node, elem=elem, elemprop=et, prop=np.vstack([[0, 0, 1, kw.get("nout", 1.0)], med]))
+    for k, v in kw.items():
+        if k == "method":
+            c["method"] = names[v]
+        elif k == "steps":
+            c["steps"] = (v, v, v)
+        elif k == "srctype":
+            c["srctype"] = int(v)
+        elif k in ("nthread",):
+            continue
+        else:
+            c[k] = v
+    c.setdefault("basisorder", 0)
+    return c
+
+
+@pytest.fixture(scope="module")
+def mesh():
+    return cases.two_media_cube()
+
+
+def test_gpu_present():
+    info = mmc.gpuinfo()
+    assert len(info) >= 1, "no CUDA device visible: the CUDA path cannot be validated"
+    assert info[0]["major"] >= 10, info[0]
+
+
+def test_rng_bit_exact_on_device():
+    """Device xorshift128+ == reference generator (src/mmc_core.cl:517-532) for the seeds the host would
+    hand out (srand(seed); rand() x4 per thread, src/mmc_cu_host.cu:438,532-534)."""
+    seeds = mmc.host_seeds(1648335518, 4 * 64).reshape(64, 4)
+    assert np.array_equal(seeds.ravel(), orc.host_seeds(1648335518, 4 * 64))
+    dev, st = mmc.rng_selftest(seeds, 257)
+    for i in (0, 1, 31, 63):
+        ref, refst = orc.rng_floats(seeds[i], 257)
+        assert np.array_equal(dev[i].view(np.uint32), ref.view(np.uint32))
+        assert np.array_equal(st[i], refst[-1])
+
+
+GPU_CASES = ["blb_elem_raw", "blb_elem_reflect", "grid_1mm", "grid_halfmm", "blb_onegate", "blb_fluence",
+             "blb_energy", "blb_detectors", "blb_isotropic", "blb_mirror"]
+
+
+@pytest.mark.parametrize("name", GPU_CASES)
+def test_statistical_parity_vs_oracle(name, mesh):
+    node, elem, et, med = mesh
+    kw = cases.case_kwargs(name)
+    N = 200000 if name != "blb_mirror" else 20000
+    kw["nphoton"] = N
+    o = orc.run(node, elem, et, med, nthread=8, gpu_semantics=1, **kw)
+    g = mmc.run(_cfg(node, elem, et, med, **kw))
+    # energy bookkeeping: launched, absorbed = tot - esc (src/mmc_cu_host.cu:988)
+    assert abs(g["energytot"][0] - o["launchweight"][0]) <= 1e-6 * N
+    fo = (o["launchweight"][0] - o["escweight"][0]) / o["launchweight"][0]
+    fg = g["energyabs"][0] / g["energytot"][0]
+    sigma = np.sqrt(max(fo * (1 - fo), 1e-4) / N)
+    assert abs(fg - fo) < 6 * sigma + 2e-4, (fg, fo, sigma)
+    # work per photon
+    assert abs(g["raytet"] / o["raytet"] - 1) < 0.02
+    # output volume: per-gate sums and the well-lit entries
+    fo_, fg_ = o["field"][..., 0], g["raw"][..., 0]
+    assert fo_.shape == fg_.shape
+    tot = fo_.sum()
+    go, gg = fo_.sum(axis=1), fg_.sum(axis=1)
+    big = go > 0.02 * tot
+    np.testing.assert_allclose(gg[big], go[big], rtol=0.03)
+    assert abs(fg_.sum() / tot - 1) < 0.02
+    cw_o, cw_g = fo_.sum(axis=0), fg_.sum(axis=0)
+    lit = cw_o > 0.02 * cw_o.max()
+    rel = np.abs(cw_g[lit] - cw_o[lit]) / cw_o[lit]
+    assert np.median(rel) < 0.05, np.median(rel)
+    assert np.mean(rel) < 0.08, np.mean(rel)
+    if kw.get("issavedet"):
+        no, ng = o["detectedcount"], len(g["detp"])
+        assert abs(no - ng) < 6 * np.sqrt(max(no, 1)) + 5, (no, ng)
+        assert g["detp"].shape[1] == o["reclen"]
+        # columns: detid, nscat[M], ppath[M], mom[M], p[3], v[3], w0
+        do, dg = o["detected"], g["detp"]
+        for col in (0, 3, 4):                      # detector id mix, partial paths
+            assert abs(do[:, col].mean() - dg[:, col].mean()) < 0.1 * max(abs(do[:, col].mean()), 0.05)
+        vn = np.linalg.norm(dg[:, -4:-1], axis=1)
+        assert np.allclose(vn, 1.0, atol=1e-4)     # exit directions are unit vectors (examples/regression/exitangle)
+        assert np.all(dg[:, -5] <= 1e-3)           # exit z on the z=0 face where the detectors sit
+
+
+def test_per_photon_seed_parity(mesh):
+    """Deterministic pairing: replay-style per-photon seeds (SEED_FROM_FILE, src/mmc_core.cl:2191-2194) make every
+    photon's stream independent of scheduling, so detected-photon rows can be matched one-to-one by their saved seed."""
+    node, elem, et, med = mesh
+    N = 20000
+    rs = np.random.RandomState(7).randint(1, 2**62, size=(N, 2)).astype(np.uint64)
+    kw = cases.case_kwargs("blb_detectors")
+    kw.update(nphoton=N, issaveseed=1)
+    o = orc.run(node, elem, et, med, nthread=8, gpu_semantics=1, seed=orc.SEED_FROM_FILE, photonseed=rs,
+                replayweight=np.ones(N, np.float32), replaytime=np.zeros(N, np.float32), **{k: v for k, v in kw.items() if k != "seed"})
+    cfg = _cfg(node, elem, et, med, **{k: v for k, v in kw.items() if k != "seed"})
+    cfg.update(replayseed=rs, replayweight=np.ones(N, np.float32), replaytime=np.zeros(N, np.float32))
+    g = mmc.run(cfg)
+    key_o = {tuple(s): i for i, s in enumerate(o["detseed"])}
+    both = [(key_o[tuple(s)], j) for j, s in enumerate(g["seeds"]) if tuple(s) in key_o]
+    assert len(both) > 0.97 * max(len(key_o), len(g["seeds"])), (len(both), len(key_o), len(g["seeds"]))
+    io, ig = np.array(both).T
+    do, dg = o["detected"][io], g["detp"][ig]
+    same = np.all(np.abs(do - dg) <= 2e-3 * np.maximum(1.0, np.abs(do)), axis=1)
+    assert same.mean() > 0.9, same.mean()        # fp rounding (fast-math vs libm) flips a few trajectories
+    assert abs(g["raw"].sum() / o["field"].sum() - 1) < 5e-3
+
+
+def test_energy_conservation_and_deposit_completeness(mesh):
+    """sum(raw energy deposits) == launched - escaped: no deposit is lost between the merged-run flushes."""
+    node, elem, et, med = mesh
+    kw = cases.case_kwargs("blb_energy")
+    kw.update(nphoton=300000, isnormalized=0)
+    g = mmc.run(_cfg(node, elem, et, med, **kw))
+    assert abs(g["raw"].sum() / g["energyabs"][0] - 1) < 2e-4
+
+
+def test_dynamic_and_static_schedules_agree(mesh):
+    node, elem, et, med = mesh
+    kw = cases.case_kwargs("blb_elem_reflect")
+    kw["nphoton"] = 300000
+    a = mmc.run(_cfg(node, elem, et, med, schedule=0, **kw))
+    b = mmc.run(_cfg(node, elem, et, med, schedule=1, **kw))
+    fa, fb = a["energyabs"][0] / a["energytot"][0], b["energyabs"][0] / b["energytot"][0]
+    assert a["energytot"][0] == b["energytot"][0] == kw["nphoton"]
+    assert abs(fa - fb) < 5e-3
+
+
+def test_full_size_cube60_anchor():
+    """BASELINE config C1 at full size (29 791 nodes / 135 000 tets, 50 gates, 1e6 photons): absorbed fraction vs the
+    reference CPU anchors recorded in BASELINE.md (17.70 % at -b 0, 27.26 % at -b 1; sigma ~0.04 %)."""
+    node, elem, et = mmc.meshgen.cube60()
+    med = [(0.005, 1.0, 0.01, 1.37)]
+    base = dict(nphoton=1000000, seed=1648335518, srcpos=(30.1, 30.2, 0.0), srcdir=(0, 0, 1), tstart=0.0, tend=5e-9,
+                tstep=1e-10, method=cases.BLBADOUEL)
+    g0 = mmc.run(_cfg(node, elem, et, med, isreflect=0, **base))
+    assert g0["e0"] == 4497                                    # examples/validation/cube.inp:7
+    assert abs(g0["energyabs"][0] / g0["energytot"][0] - 0.17704) < 2.5e-3
+    assert abs(g0["raytet"] / 1e6 - 206.9) < 3.0
+    g1 = mmc.run(_cfg(node, elem, et, med, isreflect=1, **base))
+    assert abs(g1["energyabs"][0] / g1["energytot"][0] - 0.27259) < 2.5e-3
+    assert abs(g1["raytet"] / 1e6 - 338.9) < 4.0
+
+
+def test_errors_match_reference_convention(mesh):
+    node, elem, et, med = mesh
+    kw = cases.case_kwargs("blb_elem_reflect")
+    bad = _cfg(node, elem, et, med, **kw)
+    bad["srcpos"] = (100.0, 100.0, 100.0)
+    with pytest.raises(mmc.MMCError, match="initial element does not enclose the source"):
+        mmc.run(bad)
+    bad = _cfg(node, elem, et, med, **kw)
+    bad["srcdir"] = (0, 0, 2.0)
+    with pytest.raises(mmc.MMCError, match="unitary"):
+        mmc.run(bad)
