@@ -215,19 +215,32 @@ def main():
     sess.set_field_buffer(field.data_ptr())
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def step(i):
-        flush.fill_(i & 0xFF)                      # evict the mesh and the volume from L2 between timed steps
-        torch.cuda.synchronize()
-        sess.launch(nphoton, photon_offset=0, seed=cfg["seed"], seed_offset=rank + world * i)
-        ms = sess.sync()
-        if dist is not None:
-            dist.reduce(field, dst=0, op=dist.ReduceOp.SUM)
-        return ms
+    # everything of a step (L2 flush, photon kernel, NCCL reduce, timing events) is enqueued on ONE explicit non-default
+    # stream: torch.cuda.Event only sees the stream it is recorded on, and a NULL stream handle would make the C-ABI fall
+    # back to the session's private stream
+    stream = torch.cuda.Stream(device=dev)
+
+    def step(i, timed):
+        with torch.cuda.stream(stream):
+            flush.fill_(i & 0xFF)                  # evict the mesh tables and the volume from L2 between steps
+            stream.synchronize()
+            if dist is not None and timed:
+                dist.barrier()
+                stream.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            sess.launch(nphoton, photon_offset=0, seed=cfg["seed"], seed_offset=rank + world * i, stream=stream.cuda_stream)
+            if dist is not None:
+                dist.reduce(field, dst=0, op=dist.ReduceOp.SUM)
+            e1.record(stream)
+            stream.synchronize()
+        return e0.elapsed_time(e1), sess.sync()
 
     for i in range(args.warmup):
-        step(i)
+        step(i, False)
     sess.reset()
-    field.zero_()
+    with torch.cuda.stream(stream):
+        field.zero_()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -236,20 +249,9 @@ def main():
         sampler.start()
     kern_ms, step_ms = [], []
     for i in range(args.steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        flush.fill_(i & 0xFF)
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0.record()
-        sess.launch(nphoton, photon_offset=0, seed=cfg["seed"], seed_offset=rank + world * (args.warmup + i), stream=torch.cuda.current_stream().cuda_stream)
-        if dist is not None:
-            dist.reduce(field, dst=0, op=dist.ReduceOp.SUM)
-        e1.record()
-        torch.cuda.synchronize()
-        kern_ms.append(sess.sync())
-        step_ms.append(e0.elapsed_time(e1))
+        sm, km = step(args.warmup + i, True)
+        step_ms.append(sm)
+        kern_ms.append(km)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device=dev)
     if dist is not None:

@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -45,6 +46,21 @@ int fail(int code, const char* fmt, ...) {
 
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(MMCB_ERR_CUDA, "CUDA error %d (%s) at %s:%d", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 #define CUK(call) do { int e_ = (call); if (e_ != 0) return fail(MMCB_ERR_CUDA, "CUDA error %d (%s) at %s:%d", e_, cudaGetErrorString((cudaError_t)e_), __FILE__, __LINE__); } while (0)
+
+// MMCB_TRACE=1 prints the wall-clock of every host phase to stderr (the reference prints "init complete / kernel complete /
+// transfer complete" lines with StartTimer/GetTimeMillis, src/mmc_cu_host.cu:640,749-753,875)
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    Trace() : on(getenv("MMCB_TRACE") != NULL), t(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (on) {
+            auto n = std::chrono::steady_clock::now();
+            fprintf(stderr, "[mmcb] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+            t = n;
+        }
+    }
+};
 
 const float EPSF = 1e-6f;
 const float VERY_BIG = 1e30f;
@@ -785,6 +801,7 @@ static int session_free(mmcb_session* s) {
 }
 
 static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_mesh* meshin, int device) {
+    Trace tr;
     int rc = validate(cfgin, meshin, s->cfg);
 
     if (rc) {
@@ -797,6 +814,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
         return rc;
     }
 
+    tr.mark("validate+prepare_mesh");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
 
@@ -813,6 +831,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
+    tr.mark("device+stream");
     const mmcb_config& c = s->cfg.c;
     const PrepMesh& m = s->mesh;
     s->acc_double = mmcb_k_acc_is_double() != 0;
@@ -824,6 +843,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     std::vector<mmcb_tetrec> rec;
     std::vector<float> cent;
     build_records(m, s->cfg, rec, cent);
+    tr.mark("build_records");
     rc = dev_alloc_copy(&s->d_tet, rec.data(), rec.size());
 
     if (rc) {
@@ -925,6 +945,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
         }
     }
 
+    tr.mark("alloc+upload");
     // launch shape: persistent grid = resident CTAs per SM x SM count (the reference sizes to 64 thr x 32 x #SM, src/mmc_cu_host.cu:159-163)
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
@@ -1022,6 +1043,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     a.energy = s->d_energy;
     a.raytet = s->d_raytet;
     a.photon_counter = s->d_counter;
+    tr.mark("occupancy+params");
     return 0;
 }
 
@@ -1395,6 +1417,7 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
         return fail(MMCB_ERR_INPUT, "null argument");
     }
 
+    Trace tr;
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
     const mmcb_config& c = s->cfg.c;
@@ -1437,6 +1460,8 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
         CU(cudaMemcpy(dref.data(), s->d_dref, sizeof(double) * dref.size(), cudaMemcpyDeviceToHost));
     }
 
+    tr.mark("fetch: scalars+records");
+
     if (out->field) {
         // raw sums -> double on the device (and elem->node spreading for nodal output), then one D2H copy
         std::vector<double> W(s->fieldlen);
@@ -1462,6 +1487,8 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
             cudaFree(d_tmp);
         }
 
+        tr.mark("fetch: volume D2H");
+
         if (c.isnormalized) {
             double sum = 0;
 
@@ -1476,6 +1503,8 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
         for (size_t i = 0; i < s->fieldlen; i++) {
             out->field[i] += W[i];          // cfg->exportfield[i] += field[i]  (src/mmc_cu_host.cu:918-920)
         }
+
+        tr.mark("fetch: normalise+accumulate");
     }
 
     if (out->dref && !dref.empty()) {
@@ -1492,12 +1521,14 @@ int mmcb_run_simulation(const mmcb_config* cfg, const mmcb_mesh* mesh, int devic
         return fail(MMCB_ERR_INPUT, "null output");
     }
 
+    Trace tr;
     mmcb_session* s = mmcb_create(cfg, mesh, device);
 
     if (!s) {
         return g_code ? g_code : MMCB_ERR_CUDA;
     }
 
+    tr.mark("run: create");
     int rc = 0;
     float ms = 0.f;
     const int respin = s->cfg.c.respin;
@@ -1514,14 +1545,18 @@ int mmcb_run_simulation(const mmcb_config* cfg, const mmcb_mesh* mesh, int devic
         ms += s->last_ms;
     }
 
+    tr.mark("run: launch+sync");
+
     if (rc == 0) {
         rc = mmcb_fetch(s, NULL, NULL, out);
         out->kernel_ms = ms;
     }
 
+    tr.mark("run: fetch");
     std::string keep = g_err;
     mmcb_destroy(s);
     g_err = keep;
+    tr.mark("run: destroy");
     return rc;
 }
 
