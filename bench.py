@@ -187,6 +187,10 @@ def main():
     cfg, desc = workload(args.workload, args.method)
     nphoton = int(args.photons)
     cfg["nphoton"] = nphoton
+    if os.environ.get("MMCB_HOTCACHE"):
+        cfg["hotcache"] = int(os.environ["MMCB_HOTCACHE"])
+    if os.environ.get("MMCB_BLOCK"):               # tuning runs (tools/tune.py)
+        cfg["nblocksize"] = int(os.environ["MMCB_BLOCK"])
 
     if args.impl == "reference":
         reference_arm(args, cfg, desc)

@@ -109,6 +109,8 @@ typedef struct mmcb_config {
     int   nblocksize;
     int   schedule;              /* MMCB_SCHED_* */
     int   respin;                /* repeat count, results accumulate (-r) */
+    int   hotcache;              /* CTA-private sums for the hottest 128-byte lines of the volume, picked from a pilot batch:
+                                    0 = auto (on from 500 000 photons per launch), 1 = always, -1 = never */
 } mmcb_config;
 
 typedef struct mmcb_gpuinfo {    /* src/mmc_utils.h:187-201 GPUInfo */

@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "libmmc_b200.so")
+LIBPATH = os.environ.get("MMCB_LIB") or os.path.join(HERE, "libmmc_b200.so")   # MMCB_LIB: tuning builds (tools/tune.py)
 
 SEED_FROM_FILE = -999
 MAX_SRCNUM = 16
@@ -61,7 +61,7 @@ class Config(C.Structure):
                 ("detnum", C.c_int), ("detpos", C.c_void_p), ("maxdetphoton", C.c_uint),
                 ("photonseed", C.c_void_p), ("replayweight", C.c_void_p), ("replaytime", C.c_void_p),
                 ("savetraj", C.c_int), ("maxjumpdebug", C.c_uint),
-                ("nthread", C.c_int), ("nblocksize", C.c_int), ("schedule", C.c_int), ("respin", C.c_int)]
+                ("nthread", C.c_int), ("nblocksize", C.c_int), ("schedule", C.c_int), ("respin", C.c_int), ("hotcache", C.c_int)]
 
 
 class GpuInfo(C.Structure):
@@ -207,7 +207,7 @@ DEFAULTS = dict(nphoton=0, seed=0x623F9A9E, srcpos=(0, 0, 0), srcdir=(0, 0, 1, 0
                 issaveexit=0, issaveseed=0, isspecular=0, issaveref=0, method="elem", basisorder=1,
                 outputtype="flux", roulettesize=10.0, minenergy=1e-6, nout=1.0, voidtime=1, unitinmm=1.0,
                 steps=(1.0, 1.0, 1.0), detpos=None, maxdetphoton=1000000, maxjumpdebug=10000000,
-                debuglevel="", nthread=0, nblocksize=0, schedule=0, respin=1, gpuid=1,
+                debuglevel="", nthread=0, nblocksize=0, schedule=0, respin=1, hotcache=0, gpuid=1,
                 replayseed=None, replayweight=None, replaytime=None)
 
 
@@ -269,7 +269,7 @@ class Problem:
             setattr(c, k, float(p[k]))
         for k in ("e0", "isreflect", "isnormalized", "issavedet", "ismomentum", "issaveexit", "issaveseed", "isspecular",
                   "issaveref", "basisorder", "voidtime", "maxdetphoton", "maxjumpdebug", "nthread", "nblocksize",
-                  "schedule", "respin"):
+                  "schedule", "respin", "hotcache"):
             setattr(c, k, int(p[k]))
         me, ot = p["method"], p["outputtype"]
         c.method = METHODS[me.lower()] if isinstance(me, str) else int(me)

@@ -26,20 +26,21 @@ def stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False, extra=()):
-    if not force and not stale():
+def build(force=False, verbose=False, extra=(), out=None, tag=""):
+    """out/tag: build a tuning variant (extra -D flags) into another file without touching the product library"""
+    if out is None and not force and not stale():
         return LIB
     objs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        obj = os.path.join(CSRC, src.replace(".cu", tag + ".o"))
         cmd = [NVCC] + FLAGS + list(extra) + ["-c", "-o", obj, os.path.join(CSRC, src)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))
         subprocess.check_call(cmd)
         objs.append(obj)
-    subprocess.check_call([NVCC, "-shared", "--cudart", "static", "-o", LIB] + objs)
-    return LIB
+    subprocess.check_call([NVCC, "-shared", "--cudart", "static", "-o", out or LIB] + objs)
+    return out or LIB
 
 
 if __name__ == "__main__":

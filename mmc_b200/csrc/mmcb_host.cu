@@ -26,6 +26,7 @@ extern "C" int mmcb_k_occupancy(int block, size_t smem, int isgrid, int isdet, i
 extern "C" int mmcb_k_spread_nodes(const void* efield, double* nfield, const int* elem, int ne, int nn, int maxgate, int srcnum, cudaStream_t st);
 extern "C" int mmcb_k_acc_to_double(const void* in, double* out, size_t n, cudaStream_t st);
 extern "C" int mmcb_k_acc_is_double(void);
+extern "C" int mmcb_k_hot_select(const void* field, size_t fieldlen, unsigned int* stat, void* cand, unsigned int cap, unsigned int* keys, cudaStream_t st);
 extern "C" int mmcb_k_rng(const uint32_t* dseeds, int nstream, int ndraw, float* dout, unsigned long long* dstate, cudaStream_t st);
 
 namespace {
@@ -718,7 +719,7 @@ struct mmcb_session {
     int device = 0;
     Cfg cfg;
     PrepMesh mesh;
-    mmcb_kparam kp;
+    mmcb_kparam kp, kp_pilot;
     mmcb_kargs ka;
     cudaStream_t stream = NULL;
     cudaEvent_t ev0 = NULL, ev1 = NULL;
@@ -748,7 +749,16 @@ struct mmcb_session {
     unsigned int* d_trajcount = NULL;
     double* d_energy = NULL, *d_raytet = NULL;
     unsigned long long* d_counter = NULL;
+    // hot-line cache (mmcb_types.h): keys picked once per session from a pilot batch
+    unsigned int* d_hotkeys = NULL, *d_hotstat = NULL;
+    uint2* d_hotcand = NULL;
+    bool hot_allowed = false, hot_ready = false;
+    size_t smem_base = 0;
     std::vector<uint32_t> hseeds;
+    // host seed stream position: consecutive slices (ranks/respins/bench steps) continue instead of replaying rand() from 0
+    GlibcRand* seedgen = NULL;
+    int seedgen_seed = 0;
+    size_t seedgen_pos = 0;
     uint64_t launched = 0;
 };
 
@@ -783,6 +793,10 @@ static int session_free(mmcb_session* s) {
     cudaFree(s->d_energy);
     cudaFree(s->d_raytet);
     cudaFree(s->d_counter);
+    cudaFree(s->d_hotkeys);
+    cudaFree(s->d_hotstat);
+    cudaFree(s->d_hotcand);
+    delete s->seedgen;
 
     if (s->ev0) {
         cudaEventDestroy(s->ev0);
@@ -951,7 +965,17 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     CU(cudaGetDeviceProperties(&prop, device));
     s->block = (c.nblocksize > 0) ? c.nblocksize : 128;
     s->block = std::max(32, (s->block / 32) * 32);
-    s->smem = sizeof(float4) * m.med.size() + (s->isdet ? sizeof(float) * (size_t)devreclen * s->block : 0);
+    s->smem_base = sizeof(float4) * m.med.size() + (s->isdet ? sizeof(float) * (size_t)devreclen * s->block : 0);
+    s->hot_allowed = (c.hotcache >= 0 && srcnum == 1);
+    // the grid (= number of RNG streams) is sized for the larger footprint so that pilot and main launch share it
+    s->smem = s->smem_base + (s->hot_allowed ? sizeof(unsigned int) * MMCB_HOT_SLOTS + sizeof(float) * MMCB_HOT_SLOTS * MMCB_HOT_GROUP : 0);
+
+    if (s->hot_allowed) {
+        CU(cudaMalloc(&s->d_hotkeys, sizeof(unsigned int) * MMCB_HOT_SLOTS));
+        CU(cudaMemset(s->d_hotkeys, 0xFF, sizeof(unsigned int) * MMCB_HOT_SLOTS));
+        CU(cudaMalloc(&s->d_hotstat, sizeof(unsigned int) * 34));
+        CU(cudaMalloc(&s->d_hotcand, sizeof(uint2) * 2 * MMCB_HOT_SLOTS));
+    }
 
     if (s->smem > (size_t)prop.sharedMemPerBlockOptin) {
         return fail(MMCB_ERR_LIMIT, "media table and detector records need %zu bytes of shared memory, device offers %zu", s->smem, (size_t)prop.sharedMemPerBlockOptin);
@@ -1020,6 +1044,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     k.maxjumpdebug = c.maxjumpdebug;
     k.schedule = c.schedule;
     k.nmedia = (int)m.med.size();
+    k.fieldlen = (unsigned int)s->efieldlen;
     mmcb_kargs& a = s->ka;
     memset(&a, 0, sizeof(a));
     a.tet = s->d_tet;
@@ -1030,6 +1055,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     a.med = s->d_med;
     a.srcpattern = s->d_pattern;
     a.seeds = s->d_seeds;
+    a.hotkeys = s->d_hotkeys;
     a.replayseed = s->d_replayseed;
     a.replayweight = s->d_replayweight;
     a.replaytime = s->d_replaytime;
@@ -1237,20 +1263,66 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
         return fail(MMCB_ERR_INPUT, "null session");
     }
 
+    if (nphoton >= 0xFFF00000ull) {
+        return fail(MMCB_ERR_LIMIT, "one launch takes fewer than 2^32 photons; use respin (-r) for %llu", (unsigned long long)nphoton);
+    }
+
     CU(cudaSetDevice(s->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->stream;
     // per-thread seeds: srand(seed); Pseed[j]=rand() (src/mmc_cu_host.cu:438,529-540); slices for ranks/respins
     s->hseeds.resize(4 * (size_t)s->nthread);
-    mmcb_host_seeds(seed, (size_t)seed_offset * 4 * (size_t)s->nthread, s->hseeds.size(), s->hseeds.data());
+    {
+        const size_t skip = (size_t)seed_offset * 4 * (size_t)s->nthread;
+
+        if (!s->seedgen || s->seedgen_seed != seed || s->seedgen_pos > skip) {
+            delete s->seedgen;
+            s->seedgen = new GlibcRand((unsigned int)seed);
+            s->seedgen_seed = seed;
+            s->seedgen_pos = 0;
+        }
+
+        for (; s->seedgen_pos < skip; s->seedgen_pos++) {
+            s->seedgen->next();
+        }
+
+        for (size_t i = 0; i < s->hseeds.size(); i++) {
+            s->hseeds[i] = s->seedgen->next();
+        }
+
+        s->seedgen_pos += s->hseeds.size();
+    }
+
     CU(cudaMemcpyAsync(s->d_seeds, s->hseeds.data(), s->hseeds.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
-    s->kp.nphoton = nphoton;
-    s->kp.photon_offset = photon_offset;
-    s->kp.threadphoton = (int)(nphoton / (uint64_t)s->nthread);                 // src/mmc_cu_host.cu:425-429
-    s->kp.oddphotons = (int)(nphoton - (uint64_t)s->kp.threadphoton * s->nthread);
-    CUK(mmcb_k_upload_param(&s->kp, s->cfg.detpos.data(), s->cfg.c.detnum, st));
+    const mmcb_config& c = s->cfg.c;
+    // first big launch of a session: a pilot batch (part of the requested photons) shows where the deposits pile up
+    const bool pilot = s->hot_allowed && !s->hot_ready && (c.hotcache > 0 ? nphoton >= 4096 : nphoton >= 500000);
+    uint64_t n0 = pilot ? std::min<uint64_t>(std::max<uint64_t>(nphoton / 64, 16384), 262144) : 0;
+    n0 = std::min(n0, nphoton / 2);
     CU(cudaEventRecord(s->ev0, st));
-    CUK(mmcb_k_launch_photons(&s->ka, s->grid, s->block, s->smem, s->isgrid, s->isdet, s->isgeneral, st));
+
+    for (int part = pilot ? 0 : 1; part < 2; part++) {
+        const uint64_t n = (part == 0) ? n0 : nphoton - n0, off = (part == 0) ? photon_offset : photon_offset + n0;
+        mmcb_kparam& kp = (part == 0) ? s->kp_pilot : s->kp;
+
+        if (part == 0) {
+            kp = s->kp;
+        }
+
+        kp.nphoton = n;
+        kp.photon_offset = off;
+        kp.threadphoton = (int)(n / (uint64_t)s->nthread);                 // src/mmc_cu_host.cu:425-429
+        kp.oddphotons = (int)(n - (uint64_t)kp.threadphoton * s->nthread);
+        kp.hotcache = (part == 1 && s->hot_ready) ? 1 : 0;
+        CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
+        CUK(mmcb_k_upload_param(&kp, s->cfg.detpos.data(), c.detnum, st));
+        CUK(mmcb_k_launch_photons(&s->ka, s->grid, s->block, kp.hotcache ? s->smem : s->smem_base, s->isgrid, s->isdet, s->isgeneral, st));
+
+        if (part == 0) {     // the streams continue from the states the pilot wrote back (no reseeding)
+            CUK(mmcb_k_hot_select(s->d_field, s->efieldlen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys, st));
+            s->hot_ready = true;
+        }
+    }
+
     CU(cudaEventRecord(s->ev1, st));
     s->launched += nphoton;
     return 0;

@@ -15,6 +15,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "mmcb_types.h"
 
 #ifndef MMCB_ACC_T
@@ -65,8 +67,29 @@ __device__ __forceinline__ void ld256(const void* p, float (&v)[8]) {
 __device__ __forceinline__ float sel4(const float* a, int j) {   // register-friendly a[j]
     return j == 0 ? a[0] : (j == 1 ? a[1] : (j == 2 ? a[2] : a[3]));
 }
-__device__ __forceinline__ void red_add(acc_t* p, float v) {     // no return value => RED, not ATOM
-    atomicAdd(p, (acc_t)v);
+// fire-and-forget reductions on explicitly GLOBAL addresses: atomicAdd() on a pointer loaded from a struct is a generic
+// atomic (isspacep branch + shared-memory CAS loop + returning ATOM in SASS); red.global never returns a value
+__device__ __forceinline__ void red_add(double* p, float v) {
+#ifdef MMCB_COUNT_DEPOSITS      // analysis build (tools/hotspots.py): the volume counts atomics instead of summing weights
+    v = 1.f;
+#endif
+    asm volatile("red.global.add.f64 [%0], %1;" :: "l"(__cvta_generic_to_global(p)), "d"((double)v) : "memory");
+}
+__device__ __forceinline__ void red_add(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" :: "l"(__cvta_generic_to_global(p)), "f"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int atom_add_u32(unsigned int* p, unsigned int v) {
+    unsigned int old;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(__cvta_generic_to_global(p)), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ unsigned long long atom_add_u64(unsigned long long* p, unsigned long long v) {
+    unsigned long long old;
+    asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(__cvta_generic_to_global(p)), "l"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void red_add_d(double* p, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" :: "l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
 }
 
 struct Photon {
@@ -129,26 +152,31 @@ __device__ __forceinline__ float next_scatter(float g, Photon& p, Rng& rng, floa
 
 // enclosing-element search for area sources: src/mmc_core.cl:1786-1827 (candidate list) preceded by a test of the
 // current element like the CPU path (src/mmc_raytrace.c:2599-2611)
-__device__ __noinline__ void find_launch_elem(Photon& p, const mmcb_kargs& a) {
-    const int outn[4][3] = {{0, 3, 1}, {3, 2, 1}, {0, 2, 3}, {0, 1, 2}};
-
-    for (int is = -1; is < gp.srcelemlen; is++) {
-        int cand = (is < 0) ? p.eid : a.srcelem[is];
+__device__ __noinline__ int find_launch_elem(float px, float py, float pz, int eid, const int* __restrict__ srcelem, int srcelemlen,
+        const int* __restrict__ elem, const float* __restrict__ node) {
+    // everything by value: a reference to the photon or to the kernel argument block would force both into local memory
+    for (int is = -1; is < srcelemlen; is++) {
+        int cand = (is < 0) ? eid : srcelem[is];
 
         if (cand <= 0) {
             continue;
         }
 
-        const int* ee = a.elem + 4 * (size_t)(cand - 1);
+        const int* ee = elem + 4 * (size_t)(cand - 1);
+        const int e0 = ee[0], e1 = ee[1], e2 = ee[2], e3 = ee[3];
         bool include = true;
+        #pragma unroll
 
-        for (int i = 0; i < 4; i++) {
-            const float* na = a.node + 3 * (size_t)(ee[outn[i][0]] - 1);
-            const float* nb = a.node + 3 * (size_t)(ee[outn[i][1]] - 1);
-            const float* nc = a.node + 3 * (size_t)(ee[outn[i][2]] - 1);
+        for (int i = 0; i < 4; i++) {       // faces out[i] = {0,3,1},{3,2,1},{0,2,3},{0,1,2} (src/mmc_mesh.c:59)
+            const int ia = (i == 1) ? e3 : e0;
+            const int ib = (i == 0) ? e3 : ((i == 3) ? e1 : e2);
+            const int ic = (i < 2) ? e1 : ((i == 2) ? e3 : e2);
+            const float* na = node + 3 * (size_t)(ia - 1);
+            const float* nb = node + 3 * (size_t)(ib - 1);
+            const float* nc = node + 3 * (size_t)(ic - 1);
             float abx = nb[0] - na[0], aby = nb[1] - na[1], abz = nb[2] - na[2];
             float acx = nc[0] - na[0], acy = nc[1] - na[1], acz = nc[2] - na[2];
-            float sx = p.px - na[0], sy = p.py - na[1], sz = p.pz - na[2];
+            float sx = px - na[0], sy = py - na[1], sz = pz - na[2];
             float nx = aby * acz - abz * acy, ny = abz * acx - abx * acz, nz = abx * acy - aby * acx;
             float bary = -(sx * nx + sy * ny + sz * nz);
 
@@ -158,10 +186,11 @@ __device__ __noinline__ void find_launch_elem(Photon& p, const mmcb_kargs& a) {
         }
 
         if (include) {
-            p.eid = cand;
-            return;
+            return cand;
         }
     }
+
+    return eid;
 }
 
 // launchnewphoton, src/mmc_core.cl:1417-1834 (single-slot sources; multi-slot/adjoint srcdata is out of scope)
@@ -346,7 +375,7 @@ __device__ __forceinline__ void launch_photon(Photon& p, Rng& rng, const mmcb_ka
     p.px += p.vx * EPS;                         // :1778
     p.py += p.vy * EPS;
     p.pz += p.vz * EPS;
-    find_launch_elem(p, a);
+    p.eid = find_launch_elem(p.px, p.py, p.pz, p.eid, a.srcelem, gp.srcelemlen, a.elem, a.node);
 }
 
 // Fresnel reflection / refraction, src/mmc_core.cl:1247-1303.  (nx,ny,nz): outward normal of the exit face.
@@ -398,8 +427,21 @@ __device__ __forceinline__ void reflectray(Photon& p, int& neweid, float nx, flo
 
 // deposit of a merged run (single source or photon-sharing patterns), src/mmc_core.cl:902-946
 template <bool GENERAL>
-__device__ __forceinline__ void flush_deposit(acc_t* field, unsigned int idx, float w, const Photon& p, const mmcb_kargs& a) {
+__device__ __forceinline__ void flush_deposit(acc_t* field, unsigned int idx, float w, const Photon& p, const mmcb_kargs& a,
+        bool hot, const unsigned int* hkeys, float* hvals) {
     if (!GENERAL || gp.srcnum == 1) {
+        if (hot) {          // CTA-private sum for the hottest 128-byte lines (see mmcb_types.h)
+            const unsigned int g = idx >> MMCB_HOT_GROUP_LOG2, h = MMCB_HOT_HASH(g);
+
+            if (hkeys[h] == g) {
+#ifdef MMCB_COUNT_DEPOSITS      // analysis build: only the atomics that still reach the L2 are counted
+                w = 0.f;
+#endif
+                atomicAdd(hvals + (h << MMCB_HOT_GROUP_LOG2) + (idx & (MMCB_HOT_GROUP - 1)), w);   // ATOMS CAS loop, CTA-local
+                return;
+            }
+        }
+
         red_add(field + idx, w);
     } else {
         for (int k = 0; k < gp.srcnum; k++) {
@@ -409,7 +451,7 @@ __device__ __forceinline__ void flush_deposit(acc_t* field, unsigned int idx, fl
 }
 
 __device__ __forceinline__ void savedebug(const Photon& p, const mmcb_kargs& a) {  // src/mmc_core.cl:692-704
-    unsigned int pos = atomicAdd(a.trajcount, 1u);
+    unsigned int pos = atom_add_u32(a.trajcount, 1u);
 
     if (pos < gp.maxjumpdebug) {
         float* d = a.traj + (size_t)pos * MMCB_DEBUG_REC;
@@ -426,12 +468,21 @@ __device__ __forceinline__ void savedebug(const Photon& p, const mmcb_kargs& a) 
 // the photon kernel.  GRID: dual-grid (DMMC) deposit instead of per-element; DET: detected-photon records;
 // GENERAL: area sources, photon sharing, replay, trajectories, diffuse reflectance.
 // ----------------------------------------------------------------------------------------------------
+#ifndef MMCB_MAXTHREADS
+#define MMCB_MAXTHREADS 128
+#endif
+#ifndef MMCB_MINBLOCKS
+#define MMCB_MINBLOCKS 8
+#endif
 template <bool GRID, bool DET, bool GENERAL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(MMCB_MAXTHREADS, MMCB_MINBLOCKS)
 mmcb_photon_kernel(const mmcb_kargs a) {
     extern __shared__ float4 smem4[];
     float4* smed = smem4;                                   // media table, gp.nmedia entries
-    float* ppath = (float*)(smem4 + gp.nmedia);             // DET: [reclen][blockDim]
+    unsigned int* hkeys = (unsigned int*)(smem4 + gp.nmedia);       // hot-line cache: MMCB_HOT_SLOTS keys + SLOTS*GROUP sums
+    float* hvals = (float*)(hkeys + (gp.hotcache ? MMCB_HOT_SLOTS : 0));
+    float* ppath = hvals + (gp.hotcache ? MMCB_HOT_SLOTS * MMCB_HOT_GROUP : 0);   // DET: [reclen][blockDim]
+    const bool hot = gp.hotcache != 0;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xFFFFFFFFu;
@@ -441,13 +492,23 @@ mmcb_photon_kernel(const mmcb_kargs a) {
         smed[i] = a.med[i];
     }
 
+    if (hot) {
+        for (int i = threadIdx.x; i < MMCB_HOT_SLOTS; i += blockDim.x) {
+            hkeys[i] = a.hotkeys[i];
+        }
+
+        for (int i = threadIdx.x; i < MMCB_HOT_SLOTS * MMCB_HOT_GROUP; i += blockDim.x) {
+            hvals[i] = 0.f;
+        }
+    }
+
     __syncthreads();
 
     Rng rng;
     {
-        const uint32_t* s = a.seeds + 4 * (size_t)tid;   // xorshift128p_seed, src/mmc_core.cl:545-548
-        rng.t0 = ((unsigned long long)s[0] << 32) | s[1];
-        rng.t1 = ((unsigned long long)s[2] << 32) | s[3];
+        const uint4 s = *(const uint4*)(a.seeds + 4 * (size_t)tid);   // xorshift128p_seed, src/mmc_core.cl:545-548
+        rng.t0 = ((unsigned long long)s.x << 32) | s.y;
+        rng.t1 = ((unsigned long long)s.z << 32) | s.w;
     }
     Rng initseed = rng;
 
@@ -457,14 +518,14 @@ mmcb_photon_kernel(const mmcb_kargs a) {
     int state = 0;                    // 0: needs a photon, 1: in flight, 2: no photons left
     float etot = 0.f, eesc = 0.f;     // per-thread tallies like src/mmc_core.cl:1908,2155
     unsigned int nraytet = 0;
-    // warp-level photon pool (lane 0 owns it): ids [pool_next, pool_end)
-    unsigned long long pool_next = 0, pool_end = 0;
-    // static schedule: this thread's own range
-    unsigned long long my_next = 0, my_end = 0;
+    // photon ids of this launch are 32-bit offsets (the host splits larger launches).  Dynamic schedule: lane 0 owns the warp's
+    // pool [pool_next, pool_end); static schedule: every lane owns its own range (src/mmc_core.cl:2190-2203)
+    unsigned int pool_next = 0, pool_end = 0;
+    const unsigned int nlaunch = (unsigned int)gp.nphoton;
 
     if (gp.schedule == 1) {
-        my_next = (unsigned long long)tid * gp.threadphoton + min(tid, gp.oddphotons);
-        my_end = my_next + gp.threadphoton + (tid < gp.oddphotons ? 1 : 0);
+        pool_next = (unsigned int)tid * (unsigned int)gp.threadphoton + (unsigned int)min(tid, gp.oddphotons);
+        pool_end = pool_next + (unsigned int)gp.threadphoton + (tid < gp.oddphotons ? 1u : 0u);
     }
 
     const int reclen = gp.reclen;
@@ -476,42 +537,42 @@ mmcb_photon_kernel(const mmcb_kargs a) {
         unsigned need = __ballot_sync(FULL, state == 0);
 
         if (need) {
-            unsigned long long myid = 0;
+            unsigned int myid = 0;
             bool got = false;
 
             if (gp.schedule == 1) {
-                if (state == 0 && my_next < my_end) {
-                    myid = my_next++;
+                if (state == 0 && pool_next < pool_end) {
+                    myid = pool_next++;
                     got = true;
                 }
             } else {
-                int n = __popc(need);
-                unsigned long long base = 0;
+                const int n = __popc(need);
+                unsigned int base = 0;
                 int avail = 0;
 
-                if (lane == 0 && pool_end - pool_next < (unsigned long long)n) {
+                if (lane == 0 && pool_end - pool_next < (unsigned int)n) {
                     // serve what is left of the old range first (base/avail), then open a fresh chunk
                     base = pool_next;
                     avail = (int)(pool_end - pool_next);
-                    unsigned long long want = (unsigned long long)(POOL_CHUNK + n - avail);
-                    unsigned long long g0 = atomicAdd(a.photon_counter, want);
-                    pool_next = min(g0, gp.nphoton);
-                    pool_end = max(min(g0 + want, gp.nphoton), pool_next);
+                    const unsigned int want = (unsigned int)(POOL_CHUNK + n - avail);
+                    const unsigned long long g0 = atom_add_u64(a.photon_counter, want);
+                    pool_next = (unsigned int)min(g0, (unsigned long long)nlaunch);
+                    pool_end = max((unsigned int)min(g0 + want, (unsigned long long)nlaunch), pool_next);
                 }
 
                 // broadcast the pool and distribute: first `avail` needy lanes take the leftover range, the rest the pool
                 avail = __shfl_sync(FULL, avail, 0);
                 base = __shfl_sync(FULL, base, 0);
-                unsigned long long pn = __shfl_sync(FULL, pool_next, 0);
-                unsigned long long pe = __shfl_sync(FULL, pool_end, 0);
-                int rank = __popc(need & ((1u << lane) - 1));
+                const unsigned int pn = __shfl_sync(FULL, pool_next, 0);
+                const unsigned int pe = __shfl_sync(FULL, pool_end, 0);
+                const int rank = __popc(need & ((1u << lane) - 1));
 
                 if (state == 0) {
                     if (rank < avail) {
                         myid = base + rank;
                         got = true;
                     } else {
-                        unsigned long long cand = pn + (unsigned long long)(rank - avail);
+                        const unsigned int cand = pn + (unsigned int)(rank - avail);
 
                         if (cand < pe) {
                             myid = cand;
@@ -521,14 +582,13 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 }
 
                 if (lane == 0) {
-                    unsigned long long used = (unsigned long long)max(0, n - avail);
-                    pool_next = min(pool_next + used, pool_end);
+                    pool_next = min(pool_next + (unsigned int)max(0, n - avail), pool_end);
                 }
             }
 
             if (state == 0) {
                 if (got) {
-                    p.id = (unsigned int)(myid + gp.photon_offset);
+                    p.id = myid + (unsigned int)gp.photon_offset;
 
                     if (GENERAL && gp.isreplay) {           // src/mmc_core.cl:2191-2194
                         rng.t0 = a.replayseed[2 * (size_t)p.id];
@@ -557,7 +617,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                         etot += p.w;
                     } else {
                         for (int k = 0; k < gp.srcnum; k++) {
-                            atomicAdd(a.energy + k, (double)(p.w * a.srcpattern[(size_t)p.posidx * gp.srcnum + k]));
+                            red_add_d(a.energy + k, (double)(p.w * a.srcpattern[(size_t)p.posidx * gp.srcnum + k]));
                         }
                     }
 
@@ -656,7 +716,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
 
                 if (newidx != p.oldidx) {
                     if (p.oldw > 0.f) {
-                        flush_deposit<GENERAL>(field, p.oldidx, p.oldw, p, a);
+                        flush_deposit<GENERAL>(field, p.oldidx, p.oldw, p, a, hot, hkeys, hvals);
                     }
 
                     p.oldidx = newidx;
@@ -666,7 +726,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 }
 
                 if (flushnow) {
-                    flush_deposit<GENERAL>(field, newidx, p.oldw, p, a);
+                    flush_deposit<GENERAL>(field, newidx, p.oldw, p, a, hot, hkeys, hvals);
                     p.oldw = 0.f;
                 }
             } else {                                        // dual-grid deposit :1022-1206
@@ -678,35 +738,33 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 float frac = (totalloss == 0.f) ? 0.f : (1.f - segdecay) / totalloss;
                 float segw = ww;
 
+                // consecutive segments in one voxel are merged before they reach the volume (the reference issues one atomic
+                // per segment once the photon is about to leave the element, src/mmc_core.cl:1150-1206): same sums, fewer atomics
                 for (int k = 0; k < seg; k++) {
-                    int ix = (sx > 0.f) ? __float2int_rd(sx * gp.dstep) : 0;
-                    int iy = (sy > 0.f) ? __float2int_rd(sy * gp.dstep) : 0;
-                    int iz = (sz > 0.f) ? __float2int_rd(sz * gp.dstep) : 0;
-                    unsigned int newidx = (unsigned int)(iz * gp.crop0[1] + iy * gp.crop0[0] + ix) + tshift;
-
-                    if (p.oldidx == 0xFFFFFFFFu) {
-                        p.oldidx = newidx;
-                    }
-
-                    float dep = segw * frac;
+                    const int ix = (sx > 0.f) ? __float2int_rd(sx * gp.dstep) : 0;
+                    const int iy = (sy > 0.f) ? __float2int_rd(sy * gp.dstep) : 0;
+                    const int iz = (sz > 0.f) ? __float2int_rd(sz * gp.dstep) : 0;
+                    const unsigned int newidx = (unsigned int)(iz * gp.crop0[1] + iy * gp.crop0[0] + ix) + tshift;
 
                     if (newidx != p.oldidx) {
-                        flush_deposit<GENERAL>(field, p.oldidx, p.oldw, p, a);
-                        p.oldidx = newidx;
-                        p.oldw = dep;
-                    } else {
-                        p.oldw += dep;
-                    }
+                        if (p.oldw > 0.f) {
+                            flush_deposit<GENERAL>(field, p.oldidx, p.oldw, p, a, hot, hkeys, hvals);
+                        }
 
-                    if (flushnow) {
-                        flush_deposit<GENERAL>(field, newidx, p.oldw, p, a);
+                        p.oldidx = newidx;
                         p.oldw = 0.f;
                     }
 
+                    p.oldw += segw * frac;
                     segw *= segdecay;
                     sx += dx;
                     sy += dy;
                     sz += dz;
+                }
+
+                if (flushnow && p.oldw > 0.f) {
+                    flush_deposit<GENERAL>(field, p.oldidx, p.oldw, p, a, hot, hkeys, hvals);
+                    p.oldw = 0.f;
                 }
             }
 
@@ -798,7 +856,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
             if (detect) {
                 if (GENERAL && gp.issaveref && exiteid < 0 && a.dref) {     // src/mmc_raytrace.c:2000-2003
                     int g = min((int)((p.t - gp.tstart) * gp.Rtstep), gp.maxgate - 1);
-                    atomicAdd(a.dref + ((size_t)g * gp.nf + (-exiteid - 1)), (double)p.w);
+                    red_add_d(a.dref + ((size_t)g * gp.nf + (-exiteid - 1)), (double)p.w);
                 }
 
                 if (DET) {                                  // finddetector :608-621 / wide-field :2072
@@ -826,7 +884,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 eesc += p.w;
             } else {
                 for (int k = 0; k < gp.srcnum; k++) {
-                    atomicAdd(a.energy + MMCB_MAX_SRCNUM + k, (double)(p.w * a.srcpattern[(size_t)p.posidx * gp.srcnum + k]));
+                    red_add_d(a.energy + MMCB_MAX_SRCNUM + k, (double)(p.w * a.srcpattern[(size_t)p.posidx * gp.srcnum + k]));
                 }
             }
 
@@ -843,7 +901,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 unsigned int base = 0;
 
                 if (lane == __ffs(detmask) - 1) {
-                    base = atomicAdd(a.detcount, (unsigned int)__popc(detmask));
+                    base = atom_add_u32(a.detcount, (unsigned int)__popc(detmask));
                 }
 
                 base = __shfl_sync(FULL, base, __ffs(detmask) - 1);
@@ -880,6 +938,23 @@ mmcb_photon_kernel(const mmcb_kargs a) {
     }
 
 #undef PPATH
+    // the stream state goes back in the seed-word packing: the next launch of the session may continue the streams
+    *(uint4*)(a.seeds + 4 * (size_t)tid) = make_uint4((unsigned int)(rng.t0 >> 32), (unsigned int)rng.t0, (unsigned int)(rng.t1 >> 32), (unsigned int)rng.t1);
+
+    if (hot) {              // flush the CTA-private sums of the hot lines
+        __syncthreads();
+
+        for (int i = threadIdx.x; i < MMCB_HOT_SLOTS * MMCB_HOT_GROUP; i += blockDim.x) {
+            const unsigned int g = hkeys[i >> MMCB_HOT_GROUP_LOG2];
+            const float v = hvals[i];
+            const unsigned int idx = (g << MMCB_HOT_GROUP_LOG2) + (i & (MMCB_HOT_GROUP - 1));
+
+            if (g != MMCB_HOT_EMPTY && v != 0.f && idx < gp.fieldlen) {
+                red_add(field + idx, v);
+            }
+        }
+    }
+
     // ---------------------------------------------------------------------- per-warp reduction of the tallies
     double dt = etot, de = eesc, dr = (double)nraytet;
     #pragma unroll
@@ -892,11 +967,11 @@ mmcb_photon_kernel(const mmcb_kargs a) {
 
     if (lane == 0) {
         if (!GENERAL || gp.srcnum == 1) {
-            atomicAdd(a.energy, dt);
-            atomicAdd(a.energy + MMCB_MAX_SRCNUM, de);
+            red_add_d(a.energy, dt);
+            red_add_d(a.energy + MMCB_MAX_SRCNUM, de);
         }
 
-        atomicAdd(a.raytet, dr);
+        red_add_d(a.raytet, dr);
     }
 }
 
@@ -918,7 +993,7 @@ __global__ void mmcb_spread_nodes_kernel(const acc_t* __restrict__ efield, doubl
             #pragma unroll
 
             for (int k = 0; k < 4; k++) {
-                atomicAdd(nfield + ((size_t)g * nn + (ee[k] - 1)) * srcnum + s, w);
+                red_add_d(nfield + ((size_t)g * nn + (ee[k] - 1)) * srcnum + s, w);
             }
         }
     }
@@ -928,6 +1003,158 @@ __global__ void mmcb_acc_to_double_kernel(const acc_t* __restrict__ in, double* 
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         out[i] = (double)in[i];
     }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// hot-line selection from the pilot batch (see mmcb_types.h): group = MMCB_HOT_GROUP consecutive accumulators.
+// 1) max group sum, 2) histogram of exponent distance to the max, 3) candidates down to the bin that still fits,
+// 4) direct-mapped insertion, hottest bins first.  Everything stays on the device: no host synchronisation.
+// ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float hot_group_sum(const acc_t* __restrict__ field, size_t g, size_t fieldlen) {
+    float s = 0.f;
+    const size_t i0 = g << MMCB_HOT_GROUP_LOG2;
+    #pragma unroll
+
+    for (int j = 0; j < MMCB_HOT_GROUP; j++) {
+        if (i0 + j < fieldlen) {
+            s += (float)field[i0 + j];
+        }
+    }
+
+    return s;
+}
+
+__device__ __forceinline__ int hot_bin(float s, unsigned int maxbits) {
+    return min(31, (int)((maxbits >> 23) & 0xFF) - (int)((__float_as_uint(s) >> 23) & 0xFF));
+}
+
+__device__ __forceinline__ int hot_cutbin(const unsigned int* __restrict__ hist, unsigned int cap) {
+    unsigned int cum = 0;
+    int cut = -1;
+
+    for (int b = 0; b < 32; b++) {
+        cum += hist[b];
+
+        if (cum > cap) {
+            break;
+        }
+
+        cut = b;
+    }
+
+    return cut;
+}
+
+__global__ void mmcb_hot_max_kernel(const acc_t* __restrict__ field, size_t ngroups, size_t fieldlen, unsigned int* __restrict__ stat) {
+    float m = 0.f;
+
+    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < ngroups; g += (size_t)gridDim.x * blockDim.x) {
+        m = fmaxf(m, hot_group_sum(field, g, fieldlen));
+    }
+
+    #pragma unroll
+
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    }
+
+    if ((threadIdx.x & 31) == 0 && m > 0.f) {
+        atomicMax(stat, __float_as_uint(m));      // non-negative floats order like their bit patterns
+    }
+}
+
+__global__ void mmcb_hot_hist_kernel(const acc_t* __restrict__ field, size_t ngroups, size_t fieldlen, unsigned int* __restrict__ stat) {
+    __shared__ unsigned int h[32];
+
+    if (threadIdx.x < 32) {
+        h[threadIdx.x] = 0;
+    }
+
+    __syncthreads();
+    const unsigned int maxbits = stat[0];
+
+    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < ngroups; g += (size_t)gridDim.x * blockDim.x) {
+        float s = hot_group_sum(field, g, fieldlen);
+
+        if (s > 0.f) {
+            atomicAdd(&h[hot_bin(s, maxbits)], 1u);
+        }
+    }
+
+    __syncthreads();
+
+    if (threadIdx.x < 32 && h[threadIdx.x]) {
+        atomicAdd(stat + 2 + threadIdx.x, h[threadIdx.x]);
+    }
+}
+
+// stat: [0] max bits, [1] candidate count, [2..33] histogram
+__global__ void mmcb_hot_select_kernel(const acc_t* __restrict__ field, size_t ngroups, size_t fieldlen, unsigned int* __restrict__ stat,
+                                       uint2* __restrict__ cand, unsigned int cap) {
+    const unsigned int maxbits = stat[0];
+    const int cut = hot_cutbin(stat + 2, cap);
+
+    if (cut < 0 || maxbits == 0) {
+        return;
+    }
+
+    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < ngroups; g += (size_t)gridDim.x * blockDim.x) {
+        float s = hot_group_sum(field, g, fieldlen);
+
+        if (s > 0.f) {
+            int b = hot_bin(s, maxbits);
+
+            if (b <= cut) {
+                unsigned int pos = atomicAdd(stat + 1, 1u);
+
+                if (pos < cap) {
+                    cand[pos] = make_uint2((unsigned int)g, (unsigned int)b);
+                }
+            }
+        }
+    }
+}
+
+__global__ void mmcb_hot_build_kernel(const uint2* __restrict__ cand, const unsigned int* __restrict__ stat, unsigned int cap,
+                                      unsigned int* __restrict__ keys) {
+    __shared__ unsigned int k[MMCB_HOT_SLOTS];
+
+    for (int i = threadIdx.x; i < MMCB_HOT_SLOTS; i += blockDim.x) {
+        k[i] = MMCB_HOT_EMPTY;
+    }
+
+    __syncthreads();
+    const unsigned int n = min(stat[1], cap);
+
+    for (int b = 0; b < 32; b++) {                  // hottest bins claim their slots first
+        for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
+            if (cand[i].y == (unsigned int)b) {
+                atomicCAS(&k[MMCB_HOT_HASH(cand[i].x)], MMCB_HOT_EMPTY, cand[i].x);
+            }
+        }
+
+        __syncthreads();
+    }
+
+    for (int i = threadIdx.x; i < MMCB_HOT_SLOTS; i += blockDim.x) {
+        keys[i] = k[i];
+    }
+}
+
+extern "C" int mmcb_k_hot_select(const void* field, size_t fieldlen, unsigned int* stat, void* cand, unsigned int cap, unsigned int* keys, cudaStream_t st) {
+    const size_t ngroups = (fieldlen + MMCB_HOT_GROUP - 1) >> MMCB_HOT_GROUP_LOG2;
+    const int grid = (int)std::min<size_t>(148 * 8, (ngroups + 255) / 256);
+    cudaError_t e = cudaMemsetAsync(stat, 0, sizeof(unsigned int) * 34, st);
+
+    if (e != cudaSuccess) {
+        return (int)e;
+    }
+
+    mmcb_hot_max_kernel<<<grid, 256, 0, st>>>((const acc_t*)field, ngroups, fieldlen, stat);
+    mmcb_hot_hist_kernel<<<grid, 256, 0, st>>>((const acc_t*)field, ngroups, fieldlen, stat);
+    mmcb_hot_select_kernel<<<grid, 256, 0, st>>>((const acc_t*)field, ngroups, fieldlen, stat, (uint2*)cand, cap);
+    mmcb_hot_build_kernel<<<1, 256, 0, st>>>((const uint2*)cand, stat, cap, keys);
+    return (int)cudaGetLastError();
 }
 
 // ----------------------------------------------------------------------------------------------------

@@ -7,6 +7,15 @@
 #define MMCB_MAX_TRIAL    3         // src/mmc_core.cl:355
 #define MMCB_MAX_STALL    1000      // consecutive zero-length steps before a trapped photon is dropped
 #define MMCB_DEBUG_REC    6         // floats per trajectory record (src/mmc_core.cl:360)
+// Hot-line cache: the L2 serialises atomics that hit one 128-byte line (~0.7 G red/s measured, profiles/), and every
+// photon deposits next to the source.  The hottest lines of the accumulator volume (16 doubles / 32 floats worth of
+// consecutive accumulators: MMCB_HOT_GROUP entries) are privatised per CTA in shared memory and flushed once.
+#define MMCB_HOT_GROUP_LOG2 4       // accumulators per cached group
+#define MMCB_HOT_GROUP    (1 << MMCB_HOT_GROUP_LOG2)
+#define MMCB_HOT_SLOTS_LOG2 8       // direct-mapped slots per CTA (256 x 16 floats = 16 KB + 1 KB of keys)
+#define MMCB_HOT_SLOTS    (1 << MMCB_HOT_SLOTS_LOG2)
+#define MMCB_HOT_EMPTY    0xFFFFFFFFu
+#define MMCB_HOT_HASH(g)  (((g) * 0x9E3779B1u) >> (32 - MMCB_HOT_SLOTS_LOG2))
 
 // One tetrahedron = one 96-byte record, 32-byte aligned: three 256-bit gathers (LDG.E.256) bring everything a
 // branch-less Badouel step needs -- the reference reads the same data from three arrays (normal[4*eid..],
@@ -67,6 +76,8 @@ struct mmcb_kparam {
     unsigned long long nphoton, photon_offset;
     int   threadphoton, oddphotons;
     int   nmedia;                // entries of the media table (prop+1+isextdet)
+    int   hotcache;              // 1: kargs.hotkeys holds MMCB_HOT_SLOTS group keys, deposits to those groups go to shared memory
+    unsigned int fieldlen;       // accumulator volume entries (guards the flush of the last, partial group)
 };
 
 struct mmcb_kargs {
@@ -78,7 +89,8 @@ struct mmcb_kargs {
     const int*    srcelem;
     const float4* med;           // media table (copied to shared memory by each CTA)
     const float*  srcpattern;
-    const uint32_t* seeds;       // nthread*4
+    uint32_t* seeds;             // nthread*4: seed words in, stream states out (same packing)
+    const unsigned int* hotkeys; // MMCB_HOT_SLOTS group ids (idx >> MMCB_HOT_GROUP_LOG2) or MMCB_HOT_EMPTY
     const unsigned long long* replayseed;
     const float* replayweight;
     const float* replaytime;

@@ -134,6 +134,25 @@ def test_energy_conservation_and_deposit_completeness(mesh):
     assert abs(g["raw"].sum() / g["energyabs"][0] - 1) < 2e-4
 
 
+@pytest.mark.parametrize("name", ["blb_energy", "grid_halfmm"])
+def test_hot_line_cache_loses_nothing(name, mesh):
+    """The CTA-private sums for the hottest lines (pilot batch -> key table -> shared-memory accumulation -> flush) must
+    deposit exactly what the direct red.global path deposits: energy conservation to fp32 round-off, and the same
+    volume as a run with the cache switched off (same seeds => same trajectories up to scheduling)."""
+    node, elem, et, med = mesh
+    kw = cases.case_kwargs(name)
+    kw.update(nphoton=400000, isnormalized=0, outputtype=cases.ENERGY)
+    on = mmc.run(_cfg(node, elem, et, med, hotcache=1, **kw))
+    off = mmc.run(_cfg(node, elem, et, med, hotcache=-1, **kw))
+    assert abs(on["raw"].sum() / on["energyabs"][0] - 1) < 2e-4
+    assert abs(off["raw"].sum() / off["energyabs"][0] - 1) < 2e-4
+    assert abs(on["energyabs"][0] / off["energyabs"][0] - 1) < 5e-3
+    a, b = on["raw"].reshape(-1), off["raw"].reshape(-1)
+    top = np.argsort(b)[-200:]                    # the hottest accumulators are the privatised ones
+    np.testing.assert_allclose(a[top], b[top], rtol=0.05)
+    assert abs(a[top].sum() / b[top].sum() - 1) < 0.01
+
+
 def test_dynamic_and_static_schedules_agree(mesh):
     node, elem, et, med = mesh
     kw = cases.case_kwargs("blb_elem_reflect")
