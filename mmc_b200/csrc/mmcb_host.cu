@@ -26,7 +26,8 @@ extern "C" int mmcb_k_occupancy(int block, size_t smem, int isgrid, int isdet, i
 extern "C" int mmcb_k_spread_nodes(const void* efield, double* nfield, const int* elem, int ne, int nn, int maxgate, int srcnum, cudaStream_t st);
 extern "C" int mmcb_k_acc_to_double(const void* in, double* out, size_t n, cudaStream_t st);
 extern "C" int mmcb_k_acc_is_double(void);
-extern "C" int mmcb_k_hot_select(const void* field, size_t fieldlen, unsigned int* stat, void* cand, unsigned int cap, unsigned int* keys, cudaStream_t st);
+extern "C" int mmcb_k_hot_select(const void* field, size_t fieldlen, unsigned int* stat, void* cand, unsigned int cap, unsigned int* keys,
+                                 float minshare, cudaStream_t st);
 extern "C" int mmcb_k_rng(const uint32_t* dseeds, int nstream, int ndraw, float* dout, unsigned long long* dstate, cudaStream_t st);
 
 namespace {
@@ -63,6 +64,9 @@ struct Trace {
     }
 };
 
+// the hot-line cache pays for its lookups when the hottest 128-byte line draws more than this share of the deposits
+// (a flat pilot volume, e.g. a wide disk source on a fine grid, has no line worth privatising; profiles/hotline_r1.md)
+const float MMCB_HOT_MINSHARE = 0.005f;
 const float EPSF = 1e-6f;
 const float VERY_BIG = 1e30f;
 // index tables, src/mmc_mesh.c:59-103 and src/mmc_highorder.cpp:50
@@ -973,7 +977,8 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     if (s->hot_allowed) {
         CU(cudaMalloc(&s->d_hotkeys, sizeof(unsigned int) * MMCB_HOT_SLOTS));
         CU(cudaMemset(s->d_hotkeys, 0xFF, sizeof(unsigned int) * MMCB_HOT_SLOTS));
-        CU(cudaMalloc(&s->d_hotstat, sizeof(unsigned int) * 34));
+        CU(cudaMalloc(&s->d_hotstat, sizeof(unsigned int) * MMCB_HOT_STAT_WORDS));
+        CU(cudaMemset(s->d_hotstat, 0, sizeof(unsigned int) * MMCB_HOT_STAT_WORDS));
         CU(cudaMalloc(&s->d_hotcand, sizeof(uint2) * 2 * MMCB_HOT_SLOTS));
     }
 
@@ -1056,6 +1061,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     a.srcpattern = s->d_pattern;
     a.seeds = s->d_seeds;
     a.hotkeys = s->d_hotkeys;
+    a.hotstat = s->d_hotstat;
     a.replayseed = s->d_replayseed;
     a.replayweight = s->d_replayweight;
     a.replaytime = s->d_replaytime;
@@ -1318,7 +1324,8 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
         CUK(mmcb_k_launch_photons(&s->ka, s->grid, s->block, kp.hotcache ? s->smem : s->smem_base, s->isgrid, s->isdet, s->isgeneral, st));
 
         if (part == 0) {     // the streams continue from the states the pilot wrote back (no reseeding)
-            CUK(mmcb_k_hot_select(s->d_field, s->efieldlen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys, st));
+            CUK(mmcb_k_hot_select(s->d_field, s->efieldlen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys,
+                                    c.hotcache > 0 ? 0.f : MMCB_HOT_MINSHARE, st));
             s->hot_ready = true;
         }
     }
@@ -1533,6 +1540,16 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
     }
 
     tr.mark("fetch: scalars+records");
+
+    if (tr.on && s->d_hotstat) {
+        unsigned int st[MMCB_HOT_STAT_WORDS];
+        CU(cudaMemcpy(st, s->d_hotstat, sizeof(st), cudaMemcpyDeviceToHost));
+        float mx, tot;
+        memcpy(&mx, &st[0], 4);
+        memcpy(&tot, &st[MMCB_HOT_STAT_TOTAL], 4);
+        fprintf(stderr, "[mmcb] hot-line cache: ready=%d useful=%u candidates=%u hottest line holds %.4f of the pilot weight\n", (int)s->hot_ready,
+                st[MMCB_HOT_STAT_USEFUL], st[1], tot > 0.f ? mx / tot : 0.f);
+    }
 
     if (out->field) {
         // raw sums -> double on the device (and elem->node spreading for nodal output), then one D2H copy

@@ -70,9 +70,6 @@ __device__ __forceinline__ float sel4(const float* a, int j) {   // register-fri
 // fire-and-forget reductions on explicitly GLOBAL addresses: atomicAdd() on a pointer loaded from a struct is a generic
 // atomic (isspacep branch + shared-memory CAS loop + returning ATOM in SASS); red.global never returns a value
 __device__ __forceinline__ void red_add(double* p, float v) {
-#ifdef MMCB_COUNT_DEPOSITS      // analysis build (tools/hotspots.py): the volume counts atomics instead of summing weights
-    v = 1.f;
-#endif
     asm volatile("red.global.add.f64 [%0], %1;" :: "l"(__cvta_generic_to_global(p)), "d"((double)v) : "memory");
 }
 __device__ __forceinline__ void red_add(float* p, float v) {
@@ -426,15 +423,35 @@ __device__ __forceinline__ void reflectray(Photon& p, int& neweid, float nx, flo
 }
 
 // deposit of a merged run (single source or photon-sharing patterns), src/mmc_core.cl:902-946
+// Shared-memory layout (dynamic): [hot keys: MMCB_HOT_SLOTS u32][hot sums: SLOTS*GROUP f32] when the hot-line cache is on,
+// then the media table (float4 each), then the detected-photon columns.  The cache sits at offset 0 so that its addresses
+// are immediates.
+#define MMCB_HOT_BYTES (MMCB_HOT_SLOTS * 4 + MMCB_HOT_SLOTS * MMCB_HOT_GROUP * 4)
+extern __shared__ float4 smem4[];
+
+__device__ __forceinline__ void red_global(unsigned long long gaddr, float v, double*) {
+    asm volatile("red.global.add.f64 [%0], %1;" :: "l"(gaddr), "d"((double)v) : "memory");
+}
+__device__ __forceinline__ void red_global(unsigned long long gaddr, float v, float*) {
+    asm volatile("red.global.add.f32 [%0], %1;" :: "l"(gaddr), "f"(v) : "memory");
+}
+
+// deposit of a merged run (single source or photon-sharing patterns), src/mmc_core.cl:902-946.  gfield: global-space address
+// of the accumulator volume.
 template <bool GENERAL>
-__device__ __forceinline__ void flush_deposit(acc_t* field, unsigned int idx, float w, const Photon& p, const mmcb_kargs& a,
-        bool hot, const unsigned int* hkeys, float* hvals) {
+__device__ __forceinline__ void flush_deposit(unsigned long long gfield, unsigned int idx, float w, const Photon& p, const mmcb_kargs& a, bool hot) {
+#ifdef MMCB_COUNT_DEPOSITS      // analysis build (tools/hotspots.py): the volume counts the atomics that reach the L2
+    w = 1.f;
+#endif
+
     if (!GENERAL || gp.srcnum == 1) {
         if (hot) {          // CTA-private sum for the hottest 128-byte lines (see mmcb_types.h)
+            const unsigned int* hkeys = (const unsigned int*)smem4;
+            float* hvals = (float*)smem4 + MMCB_HOT_SLOTS;
             const unsigned int g = idx >> MMCB_HOT_GROUP_LOG2, h = MMCB_HOT_HASH(g);
 
             if (hkeys[h] == g) {
-#ifdef MMCB_COUNT_DEPOSITS      // analysis build: only the atomics that still reach the L2 are counted
+#ifdef MMCB_COUNT_DEPOSITS
                 w = 0.f;
 #endif
                 atomicAdd(hvals + (h << MMCB_HOT_GROUP_LOG2) + (idx & (MMCB_HOT_GROUP - 1)), w);   // ATOMS CAS loop, CTA-local
@@ -442,10 +459,10 @@ __device__ __forceinline__ void flush_deposit(acc_t* field, unsigned int idx, fl
             }
         }
 
-        red_add(field + idx, w);
+        red_global(gfield + (unsigned long long)idx * sizeof(acc_t), w, (acc_t*)0);
     } else {
         for (int k = 0; k < gp.srcnum; k++) {
-            red_add(field + (size_t)idx * gp.srcnum + k, w * a.srcpattern[(size_t)p.posidx * gp.srcnum + k]);
+            red_global(gfield + ((unsigned long long)idx * gp.srcnum + k) * sizeof(acc_t), w * a.srcpattern[(size_t)p.posidx * gp.srcnum + k], (acc_t*)0);
         }
     }
 }
@@ -477,16 +494,16 @@ __device__ __forceinline__ void savedebug(const Photon& p, const mmcb_kargs& a) 
 template <bool GRID, bool DET, bool GENERAL>
 __global__ void __launch_bounds__(MMCB_MAXTHREADS, MMCB_MINBLOCKS)
 mmcb_photon_kernel(const mmcb_kargs a) {
-    extern __shared__ float4 smem4[];
-    float4* smed = smem4;                                   // media table, gp.nmedia entries
-    unsigned int* hkeys = (unsigned int*)(smem4 + gp.nmedia);       // hot-line cache: MMCB_HOT_SLOTS keys + SLOTS*GROUP sums
-    float* hvals = (float*)(hkeys + (gp.hotcache ? MMCB_HOT_SLOTS : 0));
-    float* ppath = hvals + (gp.hotcache ? MMCB_HOT_SLOTS * MMCB_HOT_GROUP : 0);   // DET: [reclen][blockDim]
-    const bool hot = gp.hotcache != 0;
+    const bool hot = gp.hotcache != 0 && a.hotstat[MMCB_HOT_STAT_USEFUL] != 0;
+    unsigned int* hkeys = (unsigned int*)smem4;
+    float* hvals = (float*)smem4 + MMCB_HOT_SLOTS;
+    float4* smed = smem4 + (gp.hotcache ? MMCB_HOT_BYTES / 16 : 0);     // media table, gp.nmedia entries
+    float* ppath = (float*)(smed + gp.nmedia);                  // DET: [reclen][blockDim]
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xFFFFFFFFu;
     acc_t* field = (acc_t*)a.field;
+    const unsigned long long gfield = (unsigned long long)__cvta_generic_to_global(a.field);
 
     for (int i = threadIdx.x; i < gp.nmedia; i += blockDim.x) {
         smed[i] = a.med[i];
@@ -646,19 +663,30 @@ mmcb_photon_kernel(const mmcb_kargs a) {
         ld256((const char*)rec + 32, r1);                   // nz[4] d[4]
         ld256((const char*)rec + 64, r2);                   // nb[4] type flags
         nraytet++;
-        float T[4];
+        // src/mmc_core.cl:752-771: T_j = (d_j - N_j.p) / (N_j.v) for faces with N_j.v > 0, else 1e10; the exit face is the first
+        // minimum.  The neighbour id and the outward normal of the running minimum are carried along, so the 24 record
+        // registers die here instead of living through the deposit code.
+        float Lmin = 1e10f, fnx = 0.f, fny = 0.f, fnz = 0.f;
+        int faceidx = 4, neweid = 0;
         #pragma unroll
 
-        for (int j = 0; j < 4; j++) {                       // src/mmc_core.cl:752-765
-            float S = p.vx * r0[j] + p.vy * r0[4 + j] + p.vz * r1[j];
-            float Tn = r1[4 + j] - (p.px * r0[j] + p.py * r0[4 + j] + p.pz * r1[j]);
-            T[j] = (S > 0.f) ? __fdividef(Tn, S) : 1e10f;
+        for (int j = 0; j < 4; j++) {
+            const float S = p.vx * r0[j] + p.vy * r0[4 + j] + p.vz * r1[j];
+            const float Tn = r1[4 + j] - (p.px * r0[j] + p.py * r0[4 + j] + p.pz * r1[j]);
+            const float T = (S > 0.f) ? __fdividef(Tn, S) : 1e10f;
+
+            if (T < Lmin) {
+                Lmin = T;
+                faceidx = j;
+                neweid = __float_as_int(r2[j]);
+                fnx = r0[j];
+                fny = r0[4 + j];
+                fnz = r1[j];
+            }
         }
 
-        float Lmin = fminf(fminf(fminf(T[0], T[1]), T[2]), T[3]);
-        int faceidx = (Lmin == 1e10f) ? 4 : (Lmin == T[0] ? 0 : (Lmin == T[1] ? 1 : (Lmin == T[2] ? 2 : 3)));
         const int type = __float_as_int(r2[4]);
-        const unsigned flags = __float_as_uint(r2[5]);
+        const unsigned flags = __float_as_uint(r2[5]) >> faceidx;      // bit 0: reflect, bit 4: to void, bit 8: from void
         bool terminate = false, detect = false;
         int exiteid = p.eid;          // value of r.eid at termination (<=0: left the mesh)
 
@@ -707,27 +735,25 @@ mmcb_photon_kernel(const mmcb_kargs a) {
 
             const bool flushnow = timeup || !isend;
 
-            if (!GRID) {                                    // :856-1010
-                unsigned int newidx = (unsigned int)(p.eid - 1) + tshift;
+            if (!GRID) {                                    // :856-1010: run-length merge of deposits into one accumulator
+                const unsigned int newidx = (unsigned int)(p.eid - 1) + tshift;
+                #pragma unroll
 
-                if (p.oldidx == 0xFFFFFFFFu) {
-                    p.oldidx = newidx;
-                }
+                for (int k = 0; k < 2; k++) {               // k == 1 is the closing flush (one deposit site)
+                    const unsigned int idx = (k == 0) ? newidx : (flushnow ? 0xFFFFFFFFu : newidx);
 
-                if (newidx != p.oldidx) {
-                    if (p.oldw > 0.f) {
-                        flush_deposit<GENERAL>(field, p.oldidx, p.oldw, p, a, hot, hkeys, hvals);
+                    if (idx != p.oldidx) {
+                        if (p.oldw > 0.f) {
+                            flush_deposit<GENERAL>(gfield, p.oldidx, p.oldw, p, a, hot);
+                        }
+
+                        p.oldidx = idx;
+                        p.oldw = 0.f;
                     }
 
-                    p.oldidx = newidx;
-                    p.oldw = ww;
-                } else {
-                    p.oldw += ww;
-                }
-
-                if (flushnow) {
-                    flush_deposit<GENERAL>(field, newidx, p.oldw, p, a, hot, hkeys, hvals);
-                    p.oldw = 0.f;
+                    if (k == 0) {
+                        p.oldw += ww;
+                    }
                 }
             } else {                                        // dual-grid deposit :1022-1206
                 int seg = ((int)(Lmove * gp.dstep) + 1) << 1;
@@ -739,32 +765,36 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 float segw = ww;
 
                 // consecutive segments in one voxel are merged before they reach the volume (the reference issues one atomic
-                // per segment once the photon is about to leave the element, src/mmc_core.cl:1150-1206): same sums, fewer atomics
-                for (int k = 0; k < seg; k++) {
-                    const int ix = (sx > 0.f) ? __float2int_rd(sx * gp.dstep) : 0;
-                    const int iy = (sy > 0.f) ? __float2int_rd(sy * gp.dstep) : 0;
-                    const int iz = (sz > 0.f) ? __float2int_rd(sz * gp.dstep) : 0;
-                    const unsigned int newidx = (unsigned int)(iz * gp.crop0[1] + iy * gp.crop0[0] + ix) + tshift;
+                // per segment once the photon is about to leave the element, src/mmc_core.cl:1150-1206): same sums, fewer
+                // atomics.  Pass k == seg is the closing flush, so the loop holds the only deposit site of this branch.
+                for (int k = 0; k <= seg; k++) {
+                    unsigned int newidx;
+
+                    if (k < seg) {
+                        const int ix = (sx > 0.f) ? __float2int_rd(sx * gp.dstep) : 0;
+                        const int iy = (sy > 0.f) ? __float2int_rd(sy * gp.dstep) : 0;
+                        const int iz = (sz > 0.f) ? __float2int_rd(sz * gp.dstep) : 0;
+                        newidx = (unsigned int)(iz * gp.crop0[1] + iy * gp.crop0[0] + ix) + tshift;
+                    } else {
+                        newidx = flushnow ? 0xFFFFFFFFu : p.oldidx;
+                    }
 
                     if (newidx != p.oldidx) {
                         if (p.oldw > 0.f) {
-                            flush_deposit<GENERAL>(field, p.oldidx, p.oldw, p, a, hot, hkeys, hvals);
+                            flush_deposit<GENERAL>(gfield, p.oldidx, p.oldw, p, a, hot);
                         }
 
                         p.oldidx = newidx;
                         p.oldw = 0.f;
                     }
 
-                    p.oldw += segw * frac;
-                    segw *= segdecay;
-                    sx += dx;
-                    sy += dy;
-                    sz += dz;
-                }
-
-                if (flushnow && p.oldw > 0.f) {
-                    flush_deposit<GENERAL>(field, p.oldidx, p.oldw, p, a, hot, hkeys, hvals);
-                    p.oldw = 0.f;
+                    if (k < seg) {
+                        p.oldw += segw * frac;
+                        segw *= segdecay;
+                        sx += dx;
+                        sy += dy;
+                        sz += dz;
+                    }
                 }
             }
 
@@ -784,10 +814,8 @@ mmcb_photon_kernel(const mmcb_kargs a) {
             } else if (!isend) {
                 // ---- cross the face: neighbour hop + boundary physics :1950-1990
                 // r.p0 = r.pout: already there, Lmove == Lmin on this branch
-                int neweid = __float_as_int(sel4(r2, faceidx));
-
-                if (gp.isreflect && (flags & MMCB_F_REFLECT(faceidx))) {
-                    reflectray(p, neweid, sel4(r0, faceidx), sel4(r0 + 4, faceidx), sel4(r1, faceidx), prop.w, smed, a, rng);
+                if (gp.isreflect && (flags & 1u)) {
+                    reflectray(p, neweid, fnx, fny, fnz, prop.w, smed, a, rng);
                 }
 
                 if (neweid <= 0) {
@@ -795,11 +823,11 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                     detect = true;
                     exiteid = neweid;
                 } else if (neweid != p.eid) {
-                    if ((flags & MMCB_F_FROM_VOID(faceidx)) && !gp.voidtime) {
+                    if ((flags & 0x100u) && !gp.voidtime) {
                         p.t = 0.f;                          // :1970-1978
                     }
 
-                    if ((flags & MMCB_F_TO_VOID(faceidx)) && !gp.isextdet) {
+                    if ((flags & 0x10u) && !gp.isextdet) {
                         terminate = true;                   // :1981-1990 (r.eid = 0)
                         detect = true;
                         exiteid = 0;
@@ -1046,20 +1074,24 @@ __device__ __forceinline__ int hot_cutbin(const unsigned int* __restrict__ hist,
 }
 
 __global__ void mmcb_hot_max_kernel(const acc_t* __restrict__ field, size_t ngroups, size_t fieldlen, unsigned int* __restrict__ stat) {
-    float m = 0.f;
+    float m = 0.f, tot = 0.f;
 
     for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < ngroups; g += (size_t)gridDim.x * blockDim.x) {
-        m = fmaxf(m, hot_group_sum(field, g, fieldlen));
+        const float v = hot_group_sum(field, g, fieldlen);
+        m = fmaxf(m, v);
+        tot += v;
     }
 
     #pragma unroll
 
     for (int o = 16; o > 0; o >>= 1) {
         m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+        tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
     }
 
     if ((threadIdx.x & 31) == 0 && m > 0.f) {
         atomicMax(stat, __float_as_uint(m));      // non-negative floats order like their bit patterns
+        atomicAdd((float*)(stat + MMCB_HOT_STAT_TOTAL), tot);
     }
 }
 
@@ -1115,8 +1147,8 @@ __global__ void mmcb_hot_select_kernel(const acc_t* __restrict__ field, size_t n
     }
 }
 
-__global__ void mmcb_hot_build_kernel(const uint2* __restrict__ cand, const unsigned int* __restrict__ stat, unsigned int cap,
-                                      unsigned int* __restrict__ keys) {
+__global__ void mmcb_hot_build_kernel(const uint2* __restrict__ cand, unsigned int* __restrict__ stat, unsigned int cap,
+                                      unsigned int* __restrict__ keys, float minshare) {
     __shared__ unsigned int k[MMCB_HOT_SLOTS];
 
     for (int i = threadIdx.x; i < MMCB_HOT_SLOTS; i += blockDim.x) {
@@ -1139,12 +1171,18 @@ __global__ void mmcb_hot_build_kernel(const uint2* __restrict__ cand, const unsi
     for (int i = threadIdx.x; i < MMCB_HOT_SLOTS; i += blockDim.x) {
         keys[i] = k[i];
     }
+
+    if (threadIdx.x == 0) {     // one line serialises the kernel only when it draws a sizeable share of all deposits
+        const float mx = __uint_as_float(stat[0]), tot = __uint_as_float(stat[MMCB_HOT_STAT_TOTAL]);
+        stat[MMCB_HOT_STAT_USEFUL] = (n > 0 && tot > 0.f && mx > minshare * tot) ? 1u : 0u;
+    }
 }
 
-extern "C" int mmcb_k_hot_select(const void* field, size_t fieldlen, unsigned int* stat, void* cand, unsigned int cap, unsigned int* keys, cudaStream_t st) {
+extern "C" int mmcb_k_hot_select(const void* field, size_t fieldlen, unsigned int* stat, void* cand, unsigned int cap, unsigned int* keys,
+                                 float minshare, cudaStream_t st) {
     const size_t ngroups = (fieldlen + MMCB_HOT_GROUP - 1) >> MMCB_HOT_GROUP_LOG2;
     const int grid = (int)std::min<size_t>(148 * 8, (ngroups + 255) / 256);
-    cudaError_t e = cudaMemsetAsync(stat, 0, sizeof(unsigned int) * 34, st);
+    cudaError_t e = cudaMemsetAsync(stat, 0, sizeof(unsigned int) * MMCB_HOT_STAT_WORDS, st);
 
     if (e != cudaSuccess) {
         return (int)e;
@@ -1153,7 +1191,7 @@ extern "C" int mmcb_k_hot_select(const void* field, size_t fieldlen, unsigned in
     mmcb_hot_max_kernel<<<grid, 256, 0, st>>>((const acc_t*)field, ngroups, fieldlen, stat);
     mmcb_hot_hist_kernel<<<grid, 256, 0, st>>>((const acc_t*)field, ngroups, fieldlen, stat);
     mmcb_hot_select_kernel<<<grid, 256, 0, st>>>((const acc_t*)field, ngroups, fieldlen, stat, (uint2*)cand, cap);
-    mmcb_hot_build_kernel<<<1, 256, 0, st>>>((const uint2*)cand, stat, cap, keys);
+    mmcb_hot_build_kernel<<<1, 256, 0, st>>>((const uint2*)cand, stat, cap, keys, minshare);
     return (int)cudaGetLastError();
 }
 

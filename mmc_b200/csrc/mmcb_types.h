@@ -12,9 +12,16 @@
 // consecutive accumulators: MMCB_HOT_GROUP entries) are privatised per CTA in shared memory and flushed once.
 #define MMCB_HOT_GROUP_LOG2 4       // accumulators per cached group
 #define MMCB_HOT_GROUP    (1 << MMCB_HOT_GROUP_LOG2)
-#define MMCB_HOT_SLOTS_LOG2 8       // direct-mapped slots per CTA (256 x 16 floats = 16 KB + 1 KB of keys)
+#ifndef MMCB_HOT_SLOTS_LOG2
+#define MMCB_HOT_SLOTS_LOG2 6       // direct-mapped slots per CTA (64 x 16 floats = 4 KB + 256 B of keys): the few hottest lines are what
+#endif                              // matters (measured: 64, 128 and 256 slots run the same, profiles/)
 #define MMCB_HOT_SLOTS    (1 << MMCB_HOT_SLOTS_LOG2)
 #define MMCB_HOT_EMPTY    0xFFFFFFFFu
+// selection scratch (unsigned int words): [0] bits of the largest group sum, [1] candidate count, [2..33] histogram of the
+// exponent distance to the maximum, [34] bits of the total deposited weight (float), [35] 1 when the cache is worth its lookups
+#define MMCB_HOT_STAT_WORDS 36
+#define MMCB_HOT_STAT_TOTAL 34
+#define MMCB_HOT_STAT_USEFUL 35
 #define MMCB_HOT_HASH(g)  (((g) * 0x9E3779B1u) >> (32 - MMCB_HOT_SLOTS_LOG2))
 
 // One tetrahedron = one 96-byte record, 32-byte aligned: three 256-bit gathers (LDG.E.256) bring everything a
@@ -78,6 +85,7 @@ struct mmcb_kparam {
     int   nmedia;                // entries of the media table (prop+1+isextdet)
     int   hotcache;              // 1: kargs.hotkeys holds MMCB_HOT_SLOTS group keys, deposits to those groups go to shared memory
     unsigned int fieldlen;       // accumulator volume entries (guards the flush of the last, partial group)
+    float hotshare;              // the cache is used when the hottest line holds more than this share of the deposited weight
 };
 
 struct mmcb_kargs {
@@ -91,6 +99,7 @@ struct mmcb_kargs {
     const float*  srcpattern;
     uint32_t* seeds;             // nthread*4: seed words in, stream states out (same packing)
     const unsigned int* hotkeys; // MMCB_HOT_SLOTS group ids (idx >> MMCB_HOT_GROUP_LOG2) or MMCB_HOT_EMPTY
+    const unsigned int* hotstat; // MMCB_HOT_STAT_WORDS words of the selection pass
     const unsigned long long* replayseed;
     const float* replayweight;
     const float* replaytime;

@@ -11,11 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "build", "variants")
 VARIANTS = {
-    "b128_m5": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=5"],
-    "b128_m6": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=6"],
-    "b128_m7": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=7"],
     "b128_m8": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=8"],
-    "b128_m8_f32": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=8", "-DMMCB_ACC_T=float"],
+    "b128_m9": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=9"],
+    "b128_m10": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=10"],
+    "b128_m7": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=7"],
+    "b128_m8_h7": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=8", "-DMMCB_HOT_SLOTS_LOG2=7"],
+    "b128_m8_h6": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=8", "-DMMCB_HOT_SLOTS_LOG2=6"],
 }
 
 
@@ -38,16 +39,17 @@ def main():
             continue
         block = tag.split("_")[0][1:]
         for w in wl:
-            name, method, nph = w.split(":")
-            env = dict(os.environ, MMCB_LIB=lib, MMCB_BLOCK=block)
-            env.update(EXTRA_ENV)
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", name, "--method", method, "--photons", nph,
-                                "--steps", "2", "--warmup", "1", "--no-e2e", "--no-cpu-baseline"], env=env, capture_output=True, text=True)
-            try:
-                j = json.loads(r.stdout.strip().splitlines()[-1])
-                print(json.dumps(dict(variant=tag, workload=w, photons_per_ms=round(j["value"]), kernel_ms=round(j["roofline"]["kernel_ms"], 2))), flush=True)
-            except Exception:
-                print(json.dumps(dict(variant=tag, workload=w, error=(r.stderr or r.stdout)[-300:])), flush=True)
+            for hot in ((-1, 0) if tag == "b128_m8" else (0,)):
+                name, method, nph = w.split(":")
+                env = dict(os.environ, MMCB_LIB=lib, MMCB_BLOCK=block, MMCB_HOTCACHE=str(hot))
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", name, "--method", method, "--photons", nph,
+                                    "--steps", "2", "--warmup", "1", "--no-e2e", "--no-cpu-baseline"], env=env, capture_output=True, text=True)
+                try:
+                    j = json.loads(r.stdout.strip().splitlines()[-1])
+                    print(json.dumps(dict(variant=tag, hot=hot, workload=w, photons_per_ms=round(j["value"]),
+                                          kernel_ms=round(j["roofline"]["kernel_ms"], 2))), flush=True)
+                except Exception:
+                    print(json.dumps(dict(variant=tag, workload=w, error=(r.stderr or r.stdout)[-300:])), flush=True)
 
 
 if __name__ == "__main__":
