@@ -21,8 +21,8 @@
 
 // kernel-side launchers (mmcb_kernel.cu)
 extern "C" int mmcb_k_upload_param(const mmcb_kparam* hp, const float* det4, int detnum, cudaStream_t st);
-extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int isgrid, int isdet, int isgeneral, cudaStream_t st);
-extern "C" int mmcb_k_occupancy(int block, size_t smem, int isgrid, int isdet, int isgeneral, int* blocks_per_sm);
+extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int method, int isdet, int isgeneral, cudaStream_t st);
+extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int* blocks_per_sm);
 extern "C" int mmcb_k_spread_nodes(const void* efield, double* nfield, const int* elem, int ne, int nn, int maxgate, int srcnum, cudaStream_t st);
 extern "C" int mmcb_k_acc_to_double(const void* in, double* out, size_t n, cudaStream_t st);
 extern "C" int mmcb_k_acc_is_double(void);
@@ -311,6 +311,7 @@ struct Cfg {              // validated copy of mmcb_config
     int dim[3] = {0, 0, 0};
     unsigned int crop0[3] = {0, 0, 0};
     std::vector<float> pattern, detpos;
+    float bary0[4] = {0.f, 0.f, 0.f, 0.f};     // cfg->bary0: barycentric coordinates of srcpos in e0
 };
 
 int validate(const mmcb_config* in, const mmcb_mesh* mesh, Cfg& o) {
@@ -373,8 +374,12 @@ int validate(const mmcb_config* in, const mmcb_mesh* mesh, Cfg& o) {
         c.method = MMCB_RT_BLBADOUEL;      // the GPU path offers the branch-less variant (src/mmc_utils.c:3542-3544)
     }
 
-    if (c.method != MMCB_RT_BLBADOUEL && c.method != MMCB_RT_BLBADOUEL_GRID) {
-        return fail(MMCB_ERR_INPUT, "ray tracer %d is not built into this library yet (use 's' or 'g')", c.method);
+    if (c.method < MMCB_RT_PLUCKER || c.method > MMCB_RT_BLBADOUEL_GRID) {
+        return fail(MMCB_ERR_INPUT, "unknown ray tracer %d (p, h, b, s or g)", c.method);
+    }
+
+    if ((c.method == MMCB_RT_PLUCKER || c.method == MMCB_RT_HAVEL) && c.srcnum > 1 && c.basisorder) {
+        return fail(MMCB_ERR_INPUT, "photon sharing with nodal Havel/Plucker output is not supported; use basisorder 0 or tracer 's'");
     }
 
     if (c.method == MMCB_RT_BLBADOUEL_GRID) {
@@ -531,7 +536,7 @@ int prepare_mesh(const mmcb_mesh* in, Cfg& cfg, PrepMesh& m) {
 
     // tracer_prep: initial element for point-like sources, src/mmc_mesh.c:1324-1329
     if (c.srctype == MMCB_SRC_PENCIL || c.srctype == MMCB_SRC_ISOTROPIC || c.srctype == MMCB_SRC_CONE || c.srctype == MMCB_SRC_ARCSINE) {
-        float bary[4];
+        float* bary = cfg.bary0;
 
         if (c.e0 <= 0 || barycentric(m.node.data(), m.elem.data(), m.ne, c.e0, bary, c.srcpos)) {
             c.e0 = initelem(m.node.data(), m.elem.data(), m.ne, c.srcpos, bary);
@@ -695,6 +700,70 @@ void build_records(const PrepMesh& m, const Cfg& cfg, std::vector<mmcb_tetrec>& 
     }
 }
 
+
+// Havel / Plucker tables (tracer_build, src/mmc_mesh.c:1518-1567) -> 256-byte records; neighbours, flags and type as above
+void build_records_big(const PrepMesh& m, const Cfg& cfg, const std::vector<mmcb_tetrec>& small, std::vector<mmcb_tetrec_big>& rec) {
+    static const int PAIRS[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+    rec.resize(m.ne);
+
+    for (int i = 0; i < m.ne; i++) {
+        mmcb_tetrec_big& r = rec[i];
+        memset(&r, 0, sizeof(r));
+        const int* ee = &m.elem[4 * (size_t)i];
+
+        if (cfg.c.method == MMCB_RT_HAVEL) {
+            for (int j = 0; j < 4; j++) {
+                float* vN = r.tab + 12 * j;
+                const float* a = nd(m.node.data(), ee[OUT[j][0]]), *b = nd(m.node.data(), ee[OUT[j][1]]), *c = nd(m.node.data(), ee[OUT[j][2]]);
+                float AB[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, AC[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+                float N[3] = {AB[1]* AC[2] - AB[2]* AC[1], AB[2]* AC[0] - AB[0]* AC[2], AB[0]* AC[1] - AB[1]* AC[0]};
+                float E1[3] = {AC[1]* N[2] - AC[2]* N[1], AC[2]* N[0] - AC[0]* N[2], AC[0]* N[1] - AC[1]* N[0]};   // AC x N
+                float E2[3] = {N[1]* AB[2] - N[2]* AB[1], N[2]* AB[0] - N[0]* AB[2], N[0]* AB[1] - N[1]* AB[0]};   // N x AB
+                float Rn2 = 1.f / sqrt(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
+
+                for (int k = 0; k < 3; k++) {
+                    vN[k] = Rn2 * N[k];
+                }
+
+                Rn2 *= Rn2;
+
+                for (int k = 0; k < 3; k++) {
+                    vN[4 + k] = Rn2 * E1[k];
+                    vN[8 + k] = Rn2 * E2[k];
+                }
+
+                vN[3] = vN[0] * a[0] + vN[1] * a[1] + vN[2] * a[2];
+                vN[7] = -(vN[4] * a[0] + vN[5] * a[1] + vN[6] * a[2]);
+                vN[11] = -(vN[8] * a[0] + vN[9] * a[1] + vN[10] * a[2]);
+            }
+        } else {
+            for (int j = 0; j < 6; j++) {       // d = n1 - n0, m = n0 x n1
+                const float* p0 = nd(m.node.data(), ee[PAIRS[j][0]]), *p1 = nd(m.node.data(), ee[PAIRS[j][1]]);
+                r.tab[3 * j] = p1[0] - p0[0];
+                r.tab[3 * j + 1] = p1[1] - p0[1];
+                r.tab[3 * j + 2] = p1[2] - p0[2];
+                r.tab[18 + 3 * j] = p0[1] * p1[2] - p0[2] * p1[1];
+                r.tab[18 + 3 * j + 1] = p0[2] * p1[0] - p0[0] * p1[2];
+                r.tab[18 + 3 * j + 2] = p0[0] * p1[1] - p0[1] * p1[0];
+            }
+
+            for (int j = 0; j < 4; j++) {
+                r.tab[36 + j] = small[i].nx[j];
+                r.tab[40 + j] = small[i].ny[j];
+                r.tab[44 + j] = small[i].nz[j];
+            }
+        }
+
+        for (int j = 0; j < 4; j++) {
+            r.nb[j] = small[i].nb[j];
+            r.node[j] = ee[j];
+        }
+
+        r.type = small[i].type;
+        r.flags = small[i].flags;
+    }
+}
+
 template <typename T>
 int dev_alloc_copy(T** dptr, const T* host, size_t n) {
     *dptr = NULL;
@@ -730,11 +799,12 @@ struct mmcb_session {
     float last_ms = 0.f, total_ms = 0.f;
     int grid = 0, block = 128, nthread = 0;
     size_t smem = 0;
-    bool isgrid = false, isdet = false, isgeneral = false;
+    bool isgrid = false, ishp = false, isdet = false, isgeneral = false;
     size_t fieldlen = 0, efieldlen = 0;     // output volume / kernel accumulator volume (differ for nodal BLB)
     bool acc_double = true, field_external = false;
     // device allocations
     mmcb_tetrec* d_tet = NULL;
+    mmcb_tetrec_big* d_tetbig = NULL;
     float4* d_cent = NULL;
     float* d_node = NULL;
     int* d_elem = NULL;
@@ -773,6 +843,7 @@ static int session_free(mmcb_session* s) {
 
     cudaSetDevice(s->device);
     cudaFree(s->d_tet);
+    cudaFree(s->d_tetbig);
     cudaFree(s->d_cent);
     cudaFree(s->d_node);
     cudaFree(s->d_elem);
@@ -854,6 +925,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     const PrepMesh& m = s->mesh;
     s->acc_double = mmcb_k_acc_is_double() != 0;
     s->isgrid = (c.method == MMCB_RT_BLBADOUEL_GRID);
+    s->ishp = (c.method == MMCB_RT_PLUCKER || c.method == MMCB_RT_HAVEL);
     s->isdet = c.issavedet != 0;
     s->isgeneral = !(c.srctype == MMCB_SRC_PENCIL || c.srctype == MMCB_SRC_ISOTROPIC) || c.srcnum > 1 ||
                    c.seed == MMCB_SEED_FROM_FILE || c.savetraj || c.issaveref;
@@ -866,6 +938,15 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
 
     if (rc) {
         return rc;
+    }
+
+    if (s->ishp) {
+        std::vector<mmcb_tetrec_big> big;
+        build_records_big(m, s->cfg, rec, big);
+
+        if ((rc = dev_alloc_copy(&s->d_tetbig, big.data(), big.size()))) {
+            return rc;
+        }
     }
 
     if ((rc = dev_alloc_copy((float**)&s->d_cent, cent.data(), cent.size()))) {
@@ -895,7 +976,8 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     // accumulators
     const int srcnum = c.srcnum;
     s->fieldlen = (size_t)s->cfg.datalen * s->cfg.maxgate * srcnum;
-    size_t framelen = s->isgrid ? (size_t)s->cfg.crop0[2] : (size_t)m.ne;
+    // BLB deposits per element (nodal output is spread on fetch); Havel/Plucker deposit straight into nodes for basisorder=1
+    size_t framelen = s->isgrid ? (size_t)s->cfg.crop0[2] : ((s->ishp && c.basisorder) ? (size_t)m.nn : (size_t)m.ne);
     s->efieldlen = framelen * s->cfg.maxgate * srcnum;
 
     if (s->efieldlen >= 0xFFFFFFFFull) {
@@ -987,7 +1069,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     }
 
     int bps = 0;
-    CUK(mmcb_k_occupancy(s->block, s->smem, s->isgrid, s->isdet, s->isgeneral, &bps));
+    CUK(mmcb_k_occupancy(s->block, s->smem, c.method, s->isdet, s->isgeneral, &bps));
 
     if (bps < 1) {
         return fail(MMCB_ERR_CUDA, "kernel cannot be resident with block=%d smem=%zu", s->block, s->smem);
@@ -1012,6 +1094,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     k.srcnum = srcnum;
     k.srcelemlen = (int)m.srcelem.size();
     k.e0 = c.e0;
+    memcpy(k.bary0, s->cfg.bary0, sizeof(k.bary0));
     k.focus = c.srcdir[3];
     k.tstart = c.tstart;
     k.tend = c.tend;
@@ -1053,6 +1136,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     mmcb_kargs& a = s->ka;
     memset(&a, 0, sizeof(a));
     a.tet = s->d_tet;
+    a.tetbig = s->d_tetbig;
     a.cent = s->d_cent;
     a.node = s->d_node;
     a.elem = s->d_elem;
@@ -1321,7 +1405,7 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
         kp.hotcache = (part == 1 && s->hot_ready) ? 1 : 0;
         CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
         CUK(mmcb_k_upload_param(&kp, s->cfg.detpos.data(), c.detnum, st));
-        CUK(mmcb_k_launch_photons(&s->ka, s->grid, s->block, kp.hotcache ? s->smem : s->smem_base, s->isgrid, s->isdet, s->isgeneral, st));
+        CUK(mmcb_k_launch_photons(&s->ka, s->grid, s->block, kp.hotcache ? s->smem : s->smem_base, c.method, s->isdet, s->isgeneral, st));
 
         if (part == 0) {     // the streams continue from the states the pilot wrote back (no reseeding)
             CUK(mmcb_k_hot_select(s->d_field, s->efieldlen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys,
@@ -1555,7 +1639,7 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
         // raw sums -> double on the device (and elem->node spreading for nodal output), then one D2H copy
         std::vector<double> W(s->fieldlen);
         double* d_tmp = NULL;
-        const bool nodal = (!s->isgrid && c.basisorder);
+        const bool nodal = (!s->isgrid && !s->ishp && c.basisorder);
 
         if (nodal) {
             CU(cudaMalloc(&d_tmp, sizeof(double) * s->fieldlen));

@@ -481,8 +481,296 @@ __device__ __forceinline__ void savedebug(const Photon& p, const mmcb_kargs& a) 
     }
 }
 
+
 // ----------------------------------------------------------------------------------------------------
-// the photon kernel.  GRID: dual-grid (DMMC) deposit instead of per-element; DET: detected-photon records;
+// Havel and Plucker ray-tetrahedron steps with the semantics of the reference's CPU file, which is their only
+// implementation (src/mmc_raytrace.c:531-800 havel_raytet, :227-508 plucker_raytet):
+// ">=" time-window test, one deposit per step (no run-length merge), barycentric nodal deposit for basisorder=1 with the
+// entry coordinates bary0 carried from element to element by matching global node ids.
+// ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld128(const void* p, float (&v)[4]) {
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ bool samesign(float a, float b) {     // !((a ^ b) & sign bit), src/mmc_raytrace.c:540-555
+    return ((__float_as_uint(a) ^ __float_as_uint(b)) & 0x80000000u) == 0;
+}
+
+
+// barycentric coordinates of the launch point in its element for the nodal Havel/Plucker deposit: cfg->bary0 for point
+// sources (mesh_barycentric on the host), recomputed for area sources like src/mmc_raytrace.c:2613-2640
+__device__ __forceinline__ float4 launch_bary(const Photon& p, const mmcb_kargs& a) {
+    if (gp.basisorder == 0) {
+        return make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    if (gp.srctype == 0 || (p.eid == gp.e0 && (gp.srctype == 1 || gp.srctype == 2 || gp.srctype == 7))) {
+        return make_float4(gp.bary0[0], gp.bary0[1], gp.bary0[2], gp.bary0[3]);
+    }
+
+    const int4 e = *(const int4*)(a.elem + 4 * (size_t)(p.eid - 1));
+    const int id[4] = {e.x, e.y, e.z, e.w};
+    float q[4][3];
+    #pragma unroll
+
+    for (int i = 0; i < 4; i++) {
+        q[i][0] = a.node[3 * (size_t)(id[i] - 1)];
+        q[i][1] = a.node[3 * (size_t)(id[i] - 1) + 1];
+        q[i][2] = a.node[3 * (size_t)(id[i] - 1) + 2];
+    }
+
+    const int outn[4][3] = {{0, 3, 1}, {3, 2, 1}, {0, 2, 3}, {0, 1, 2}}, fmap[4] = {2, 0, 1, 3};
+    float b[4], s = 0.f;
+    #pragma unroll
+
+    for (int i = 0; i < 4; i++) {
+        const float* na = q[outn[i][0]], *nb = q[outn[i][1]], *nc = q[outn[i][2]];
+        float abx = nb[0] - na[0], aby = nb[1] - na[1], abz = nb[2] - na[2];
+        float acx = nc[0] - na[0], acy = nc[1] - na[1], acz = nc[2] - na[2];
+        float sx = p.px - na[0], sy = p.py - na[1], sz = p.pz - na[2];
+        b[fmap[i]] = -(sx * (aby * acz - abz * acy) + sy * (abz * acx - abx * acz) + sz * (abx * acy - aby * acx));
+    }
+
+    s = b[0] + b[1] + b[2] + b[3];
+    return make_float4(b[0] / s, b[1] / s, b[2] / s, b[3] / s);
+}
+
+template <int METHOD, bool GENERAL>
+__device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kargs& a, const float4* smed, unsigned long long gfield, bool hot,
+                                        bool& found, float& Lmove, bool& isend, bool& timeup, int& neweid, float& fnx, float& fny, float& fnz,
+                                        int& type, unsigned& flags, float4& prop) {
+    const mmcb_tetrec_big* rec = a.tetbig + (p.eid - 1);
+    float tail[8];              // nb[4] node[4]
+    ld256(rec->nb, tail);
+    const int2 tf = *(const int2*)&rec->type;
+    type = tf.x;
+    int fi = -1;                // tracer face 0..3
+    float Lp0 = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;      // barycentric coordinates of the exit point (local node order)
+
+    if constexpr (METHOD == 1) {
+        // ---- Havel: first face (in order) with det >= 0, 0 <= t <= 1e10, and the hit inside the triangle
+        float tu = 0.f, tv = 0.f;
+        #pragma unroll
+
+        for (int i = 0; i < 4; i++) {
+            float n[4], e1[4], e2[4];
+            ld128(rec->tab + 12 * i, n);
+            ld128(rec->tab + 12 * i + 4, e1);
+            ld128(rec->tab + 12 * i + 8, e2);
+
+            if (fi < 0) {
+                const float det = n[0] * p.vx + n[1] * p.vy + n[2] * p.vz;
+
+                if (!(__float_as_uint(det) & 0x80000000u)) {
+                    const float dett = (-n[0] * p.px + -n[1] * p.py) + (-n[2] * p.pz + n[3]);
+
+                    if (samesign(dett, 1e10f * det - dett)) {
+                        const float qx = p.px * det + dett * p.vx, qy = p.py * det + dett * p.vy, qz = p.pz * det + dett * p.vz;   // w = det
+                        const float detu = (qx * e1[0] + qy * e1[1]) + (qz * e1[2] + det * e1[3]);
+
+                        if (samesign(detu, det - detu)) {
+                            const float detv = (qx * e2[0] + qy * e2[1]) + (qz * e2[2] + det * e2[3]);
+
+                            if (samesign(detv, det - (detu + detv))) {
+                                const float inv = 1.f / det;
+                                const float t = dett * inv;
+
+                                if (t == t) {
+                                    fi = i;
+                                    Lp0 = t;
+                                    tu = detu * inv;
+                                    tv = detv * inv;
+                                    fnx = n[0];
+                                    fny = n[1];
+                                    fnz = n[2];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        // exit barycentrics: b[out[i][0]] = 1-u-v, b[out[i][1]] = u, b[out[i][2]] = v, b[facemap[i]] = 0 (:696-699)
+        const float w0 = 1.f - tu - tv;
+        b0 = (fi == 1) ? 0.f : w0;
+        b1 = (fi == 2) ? 0.f : ((fi == 3) ? tu : tv);
+        b2 = (fi == 0) ? 0.f : ((fi == 3) ? tv : tu);
+        b3 = (fi == 0) ? tu : ((fi == 1) ? w0 : ((fi == 2) ? tv : 0.f));
+    } else {
+        // ---- Plucker: w_i = v.m_i + (p x (p+v)).d_i for the 6 edges, sign pattern per face (:283-343)
+        const float cx = p.py * (p.pz + p.vz) - p.pz * (p.py + p.vy);
+        const float cy = p.pz * (p.px + p.vx) - p.px * (p.pz + p.vz);
+        const float cz = p.px * (p.py + p.vy) - p.py * (p.px + p.vx);
+        float w[6];
+        #pragma unroll
+
+        for (int i = 0; i < 6; i++) {        // tab: d[6][3] then m[6][3]
+            const float* D = rec->tab + 3 * i, *Mv = rec->tab + 18 + 3 * i;
+            w[i] = (p.vx * __ldg(Mv) + p.vy * __ldg(Mv + 1) + p.vz * __ldg(Mv + 2)) + (cx * __ldg(D) + cy * __ldg(D + 1) + cz * __ldg(D + 2));
+        }
+
+        // fc = {{0,4,2},{3,5,4},{2,5,1},{1,3,0}}; faces 2 and 3 negate their middle edge first (:299-301)
+        const float fa[4] = {w[0], w[3], w[2], w[1]}, fb[4] = {w[4], w[5], -w[5], -w[3]}, fcc[4] = {w[2], w[4], w[1], w[0]};
+        float wa = 0.f, wb = 0.f, wc = 0.f;
+        #pragma unroll
+
+        for (int i = 0; i < 4; i++) {
+            if (fi < 0 && (__float_as_uint(fa[i]) & __float_as_uint(fb[i]) & (__float_as_uint(fcc[i]) ^ 0x80000000u) & 0x80000000u)) {
+                fi = i;
+                wa = fa[i];
+                wb = fb[i];
+                wc = fcc[i];
+            }
+        }
+
+        if (fi >= 0) {
+            // nc = {{3,0,1},{3,1,2},{2,0,3},{1,0,2}}: b[nc0] = -wa Rv, b[nc1] = -wb Rv, b[nc2] = wc Rv
+            const float Rv = 1.f / (-wa - wb + wc);
+            const float ba = -wa * Rv, bb = -wb * Rv, bc = wc * Rv;
+            b0 = (fi == 0) ? bb : ((fi == 1) ? 0.f : bb);
+            b1 = (fi == 0) ? bc : ((fi == 1) ? bb : ((fi == 2) ? 0.f : ba));
+            b2 = (fi == 0) ? 0.f : ((fi == 1) ? bc : ((fi == 2) ? ba : bc));
+            b3 = (fi == 0) ? ba : ((fi == 1) ? ba : ((fi == 2) ? bc : 0.f));
+            // pout = sum_k b_k node_k over the three nodes of the exit face (getinterp, :165-169)
+            const int n0 = __float_as_int(tail[4]), n1 = __float_as_int(tail[5]), n2 = __float_as_int(tail[6]), n3 = __float_as_int(tail[7]);
+            const int ia = (fi == 2) ? n2 : ((fi == 3) ? n1 : n3), ib = (fi == 1) ? n1 : n0, ic = (fi == 0) ? n1 : ((fi == 2) ? n3 : n2);
+            const float* qa = a.node + 3 * (size_t)(ia - 1), *qb = a.node + 3 * (size_t)(ib - 1), *qc = a.node + 3 * (size_t)(ic - 1);
+            ox = ba * __ldg(qa) + bb * __ldg(qb) + bc * __ldg(qc);
+            oy = ba * __ldg(qa + 1) + bb * __ldg(qb + 1) + bc * __ldg(qc + 1);
+            oz = ba * __ldg(qa + 2) + bb * __ldg(qb + 2) + bc * __ldg(qc + 2);
+            Lp0 = sqrtf((ox - p.px) * (ox - p.px) + (oy - p.py) * (oy - p.py) + (oz - p.pz) * (oz - p.pz));
+            // outward face normals (BLB table: reflectray reads mesh->n for this tracer, :2272-2276): tab[36..47] = nx[4] ny[4] nz[4]
+            fnx = __ldg(rec->tab + 36 + fi);
+            fny = __ldg(rec->tab + 40 + fi);
+            fnz = __ldg(rec->tab + 44 + fi);
+        }
+    }
+
+    found = (fi >= 0);
+
+    if (!found) {
+        return;
+    }
+
+    flags = ((unsigned)tf.y) >> fi;
+    prop = smed[type];
+    const float mus = prop.y;
+    const float dlen = (mus <= EPS) ? R_MIN_MUS : p.slen / mus;
+    isend = (Lp0 > dlen);
+    Lmove = isend ? dlen : Lp0;
+    neweid = __float_as_int((fi == 0) ? tail[0] : ((fi == 1) ? tail[1] : ((fi == 2) ? tail[2] : tail[3])));
+    const float rc = prop.w * R_C0;
+
+    // common step tail, src/mmc_raytrace.c:357-388 / :633-664 (">=" window test)
+    if ((int)((p.t + Lmove * rc - gp.tstart) * gp.Rtstep) >= (int)((gp.tend - gp.tstart) * gp.Rtstep)) {
+        timeup = true;
+        Lmove = (gp.tend - p.t) / rc - 1e-4f;
+    }
+
+    float currweight = p.w;
+    p.w *= __expf(-prop.x * Lmove);
+
+    if (GENERAL && gp.isreplay) {
+        if (gp.outputtype == 3) {               // otJacobian: CPU semantics exp(-DELTA_MUA L) (:1523-1526 equivalent lines)
+            currweight = __expf(-DELTA_MUA * Lmove) * a.replayweight[p.id] + p.w;
+        } else if (gp.outputtype == 4) {
+            currweight = Lmove * a.replayweight[p.id] + p.w;
+        }
+    }
+
+    p.slen -= Lmove * mus;
+
+    if (GENERAL && gp.isreplay && gp.outputtype == 5) {
+        currweight = ((p.slen0 < EPS) ? 1.f : (Lmove * mus / p.slen0)) * a.replayweight[p.id] + p.w;
+    }
+
+    const bool fluence = (gp.outputtype != 2 && gp.outputtype != 4 && gp.outputtype != 5);
+    const bool nodal = gp.basisorder != 0;
+
+    if constexpr (METHOD == 1) {
+        if (Lp0 == 0.f) {       // :666-668: early break -- no deposit, no clock advance; the photon hops on
+            Lmove = 0.f;
+            return;
+        }
+
+        p.px += Lmove * p.vx;
+        p.py += Lmove * p.vy;
+        p.pz += Lmove * p.vz;
+    } else {
+        if (!isend && !timeup) {        // crossing: the hop continues from the interpolated exit point (src/mmc_raytrace.c:1895)
+            p.px = ox;
+            p.py = oy;
+            p.pz = oz;
+        } else {
+            p.px += Lmove * p.vx;
+            p.py += Lmove * p.vy;
+            p.pz += Lmove * p.vz;
+        }
+
+        if (nodal && !(Lp0 > EPS)) {    // :430: nodal Plucker skips degenerate steps entirely (the position still advances)
+            return;
+        }
+    }
+
+    float ww = currweight - p.w;
+    p.t += Lmove * rc;
+
+    if (fluence) {
+        ww = (prop.x < EPS) ? (currweight * Lmove) : (ww / prop.x);
+    }
+
+    int gate;
+
+    if (GENERAL && (gp.outputtype == 4 || gp.outputtype == 5)) {
+        gate = min((int)(a.replaytime[p.id] * gp.Rtstep), gp.maxgate - 1);
+    } else {
+        gate = min((int)((p.t - gp.tstart) * gp.Rtstep), gp.maxgate - 1);
+    }
+
+    const unsigned int tshift = (unsigned int)gate * gp.framelen;
+
+    if (!nodal) {
+        flush_deposit<GENERAL>(gfield, (unsigned int)(p.eid - 1) + tshift, ww, p, a, hot);
+        return;
+    }
+
+    // ---- nodal deposit: w/2 (bary_in + bary_end) to the four nodes; bary_end is the exit point or, when the path ends
+    //      inside, the point reached (:709-720,763-780 Havel; :456-480 Plucker)
+    const float ratio = Lmove / Lp0;
+
+    if (isend) {
+        b0 = b0 * ratio + bary0.x * (1.f - ratio);
+        b1 = b1 * ratio + bary0.y * (1.f - ratio);
+        b2 = b2 * ratio + bary0.z * (1.f - ratio);
+        b3 = b3 * ratio + bary0.w * (1.f - ratio);
+    }
+
+    const int n0 = __float_as_int(tail[4]), n1 = __float_as_int(tail[5]), n2 = __float_as_int(tail[6]), n3 = __float_as_int(tail[7]);
+
+    if (METHOD == 1 || prop.x > 0.f || fluence) {
+        const float h = ww * 0.5f;
+        flush_deposit<GENERAL>(gfield, (unsigned int)(n0 - 1) + tshift, (bary0.x + b0) * h, p, a, hot);
+        flush_deposit<GENERAL>(gfield, (unsigned int)(n1 - 1) + tshift, (bary0.y + b1) * h, p, a, hot);
+        flush_deposit<GENERAL>(gfield, (unsigned int)(n2 - 1) + tshift, (bary0.z + b2) * h, p, a, hot);
+        flush_deposit<GENERAL>(gfield, (unsigned int)(n3 - 1) + tshift, (bary0.w + b3) * h, p, a, hot);
+    }
+
+    // entry coordinates of the next step: same point, renumbered to the neighbour's node order when the face is crossed
+    if (!isend && neweid > 0) {
+        const int4 nx = *(const int4*)(a.tetbig[neweid - 1].node);
+        bary0.x = ((n0 == nx.x) ? b0 : 0.f) + ((n1 == nx.x) ? b1 : 0.f) + ((n2 == nx.x) ? b2 : 0.f) + ((n3 == nx.x) ? b3 : 0.f);
+        bary0.y = ((n0 == nx.y) ? b0 : 0.f) + ((n1 == nx.y) ? b1 : 0.f) + ((n2 == nx.y) ? b2 : 0.f) + ((n3 == nx.y) ? b3 : 0.f);
+        bary0.z = ((n0 == nx.z) ? b0 : 0.f) + ((n1 == nx.z) ? b1 : 0.f) + ((n2 == nx.z) ? b2 : 0.f) + ((n3 == nx.z) ? b3 : 0.f);
+        bary0.w = ((n0 == nx.w) ? b0 : 0.f) + ((n1 == nx.w) ? b1 : 0.f) + ((n2 == nx.w) ? b2 : 0.f) + ((n3 == nx.w) ? b3 : 0.f);
+    } else if (METHOD == 1 || isend) {
+        bary0 = make_float4(b0, b1, b2, b3);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// the photon kernel.  METHOD: ray tracer (0 Plucker, 1 Havel, 3 branch-less Badouel, 4 BLB with dual-grid (DMMC) deposit;
+// enum TRTMethod, src/mmc_utils.h); DET: detected-photon records;
 // GENERAL: area sources, photon sharing, replay, trajectories, diffuse reflectance.
 // ----------------------------------------------------------------------------------------------------
 #ifndef MMCB_MAXTHREADS
@@ -491,9 +779,14 @@ __device__ __forceinline__ void savedebug(const Photon& p, const mmcb_kargs& a) 
 #ifndef MMCB_MINBLOCKS
 #define MMCB_MINBLOCKS 8
 #endif
-template <bool GRID, bool DET, bool GENERAL>
-__global__ void __launch_bounds__(MMCB_MAXTHREADS, MMCB_MINBLOCKS)
+#ifndef MMCB_MINBLOCKS_HP
+#define MMCB_MINBLOCKS_HP 4
+#endif
+template <int METHOD, bool DET, bool GENERAL>
+__global__ void __launch_bounds__(MMCB_MAXTHREADS, (METHOD <= 1) ? MMCB_MINBLOCKS_HP : MMCB_MINBLOCKS)
 mmcb_photon_kernel(const mmcb_kargs a) {
+    constexpr bool GRID = (METHOD == 4);
+    constexpr bool HP = (METHOD <= 1);          // Havel / Plucker: 256-byte records, CPU-file semantics (src/mmc_raytrace.c)
     const bool hot = gp.hotcache != 0 && a.hotstat[MMCB_HOT_STAT_USEFUL] != 0;
     unsigned int* hkeys = (unsigned int*)smem4;
     float* hvals = (float*)smem4 + MMCB_HOT_SLOTS;
@@ -532,6 +825,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
     Photon p;
     p.eid = 0;
     p.w = 0.f;
+    float4 bary0 = make_float4(0.f, 0.f, 0.f, 0.f);     // HP nodal deposit: barycentric coordinates of the step's start point
     int state = 0;                    // 0: needs a photon, 1: in flight, 2: no photons left
     float etot = 0.f, eesc = 0.f;     // per-thread tallies like src/mmc_core.cl:1908,2155
     unsigned int nraytet = 0;
@@ -622,6 +916,10 @@ mmcb_photon_kernel(const mmcb_kargs a) {
 
                     launch_photon<GENERAL>(p, rng, a);
 
+                    if constexpr (HP) {
+                        bary0 = launch_bary(p, a);
+                    }
+
                     if (DET) {
                         if (!GENERAL || gp.srctype != 5 || gp.srcnum == 1) {
                             PPATH(reclen - 1) = p.w;                       // :1894-1898
@@ -657,17 +955,26 @@ mmcb_photon_kernel(const mmcb_kargs a) {
 
         if (state == 1) {
         // ------------------------------------------------------------------ one ray-tetrahedron step
+        nraytet++;
+        float Lmove = 0.f, fnx = 0.f, fny = 0.f, fnz = 0.f;
+        float4 prop = make_float4(0.f, 0.f, 0.f, 1.f);
+        int neweid = 0, type = 0;
+        unsigned flags = 0;
+        bool found = false, isend = false, timeup = false;
+        bool terminate = false, detect = false;
+        int exiteid = p.eid;          // value of r.eid at termination (<=0: left the mesh)
+
+        if constexpr (!HP) {
         const mmcb_tetrec* rec = a.tet + (p.eid - 1);
         float r0[8], r1[8], r2[8];
         ld256(rec, r0);                                     // nx[4] ny[4]
         ld256((const char*)rec + 32, r1);                   // nz[4] d[4]
         ld256((const char*)rec + 64, r2);                   // nb[4] type flags
-        nraytet++;
         // src/mmc_core.cl:752-771: T_j = (d_j - N_j.p) / (N_j.v) for faces with N_j.v > 0, else 1e10; the exit face is the first
         // minimum.  The neighbour id and the outward normal of the running minimum are carried along, so the 24 record
         // registers die here instead of living through the deposit code.
-        float Lmin = 1e10f, fnx = 0.f, fny = 0.f, fnz = 0.f;
-        int faceidx = 4, neweid = 0;
+        float Lmin = 1e10f;
+        int faceidx = 4;
         #pragma unroll
 
         for (int j = 0; j < 4; j++) {
@@ -685,18 +992,16 @@ mmcb_photon_kernel(const mmcb_kargs a) {
             }
         }
 
-        const int type = __float_as_int(r2[4]);
-        const unsigned flags = __float_as_uint(r2[5]) >> faceidx;      // bit 0: reflect, bit 4: to void, bit 8: from void
-        bool terminate = false, detect = false;
-        int exiteid = p.eid;          // value of r.eid at termination (<=0: left the mesh)
+        type = __float_as_int(r2[4]);
+        flags = __float_as_uint(r2[5]) >> faceidx;      // bit 0: reflect, bit 4: to void, bit 8: from void
+        found = (faceidx < 4 && Lmin >= 0.f);
 
-        if (faceidx < 4 && Lmin >= 0.f) {
-            const float4 prop = smed[type];                 // mua mus g n
-            float Lmove = (prop.y <= EPS) ? R_MIN_MUS : __fdividef(p.slen, prop.y);
-            const bool isend = (Lmin > Lmove);
+        if (found) {
+            prop = smed[type];                              // mua mus g n
+            Lmove = (prop.y <= EPS) ? R_MIN_MUS : __fdividef(p.slen, prop.y);
+            isend = (Lmin > Lmove);
             Lmove = isend ? Lmove : Lmin;
             const float rc = prop.w * R_C0;
-            bool timeup = false;
 
             if ((int)((p.t + Lmove * rc - gp.tstart) * gp.Rtstep) > gp.maxgate - 1) {   // :803-807
                 timeup = true;
@@ -798,9 +1103,18 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 }
             }
 
-            p.px += Lmove * p.vx;                           // :1222
-            p.py += Lmove * p.vy;
-            p.pz += Lmove * p.vz;
+        }   // found
+        } else {
+            hp_step<METHOD, GENERAL>(p, bary0, a, smed, gfield, hot, found, Lmove, isend, timeup, neweid, fnx, fny, fnz, type, flags, prop);
+        }
+
+        if (found) {
+            if constexpr (!HP) {
+                p.px += Lmove * p.vx;                       // :1222
+                p.py += Lmove * p.vy;
+                p.pz += Lmove * p.vz;
+            }
+
             // progress guard (not in the reference): a photon that makes no headway for MMCB_MAX_STALL consecutive steps is
             // trapped between degenerate/inverted tetrahedra (the reference CPU path spins forever there) and is dropped
             p.fixcount = (Lmove > 0.f) ? 0 : (p.fixcount + 0x100);
@@ -1208,89 +1522,52 @@ extern "C" int mmcb_k_upload_param(const mmcb_kparam* hp, const float* det4, int
     return (int)e;
 }
 
-template <bool GRID, bool DET, bool GENERAL>
-static int launch_variant(const mmcb_kargs& a, int grid, int block, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(mmcb_photon_kernel<GRID, DET, GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// one entry per (tracer, detection, general-source) combination
+typedef void (*photon_kernel_t)(const mmcb_kargs);
+template <int METHOD>
+static photon_kernel_t pick_kernel(int isdet, int isgeneral) {
+    if (isdet) {
+        return isgeneral ? mmcb_photon_kernel<METHOD, true, true> : mmcb_photon_kernel<METHOD, true, false>;
+    }
+
+    return isgeneral ? mmcb_photon_kernel<METHOD, false, true> : mmcb_photon_kernel<METHOD, false, false>;
+}
+static photon_kernel_t pick_kernel(int method, int isdet, int isgeneral) {
+    switch (method) {
+        case 0:
+            return pick_kernel<0>(isdet, isgeneral);
+
+        case 1:
+            return pick_kernel<1>(isdet, isgeneral);
+
+        case 4:
+            return pick_kernel<4>(isdet, isgeneral);
+
+        default:
+            return pick_kernel<3>(isdet, isgeneral);
+    }
+}
+
+extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int method, int isdet, int isgeneral, cudaStream_t st) {
+    photon_kernel_t k = pick_kernel(method, isdet, isgeneral);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 
     if (e != cudaSuccess) {
         return (int)e;
     }
 
-    mmcb_photon_kernel<GRID, DET, GENERAL><<<grid, block, smem, st>>>(a);
+    k<<<grid, block, smem, st>>>(*a);
     return (int)cudaGetLastError();
 }
 
-extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int isgrid, int isdet, int isgeneral, cudaStream_t st) {
-    int v = (isgrid ? 4 : 0) | (isdet ? 2 : 0) | (isgeneral ? 1 : 0);
+extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int* blocks_per_sm) {
+    photon_kernel_t k = pick_kernel(method, isdet, isgeneral);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 
-    switch (v) {
-        case 0:
-            return launch_variant<false, false, false>(*a, grid, block, smem, st);
-
-        case 1:
-            return launch_variant<false, false, true>(*a, grid, block, smem, st);
-
-        case 2:
-            return launch_variant<false, true, false>(*a, grid, block, smem, st);
-
-        case 3:
-            return launch_variant<false, true, true>(*a, grid, block, smem, st);
-
-        case 4:
-            return launch_variant<true, false, false>(*a, grid, block, smem, st);
-
-        case 5:
-            return launch_variant<true, false, true>(*a, grid, block, smem, st);
-
-        case 6:
-            return launch_variant<true, true, false>(*a, grid, block, smem, st);
-
-        default:
-            return launch_variant<true, true, true>(*a, grid, block, smem, st);
-    }
-}
-
-extern "C" int mmcb_k_occupancy(int block, size_t smem, int isgrid, int isdet, int isgeneral, int* blocks_per_sm) {
-    int v = (isgrid ? 4 : 0) | (isdet ? 2 : 0) | (isgeneral ? 1 : 0);
-    cudaError_t e;
-#define OCC(G, D, N) e = cudaFuncSetAttribute(mmcb_photon_kernel<G, D, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, mmcb_photon_kernel<G, D, N>, block, smem)
-
-    switch (v) {
-        case 0:
-            OCC(false, false, false);
-            break;
-
-        case 1:
-            OCC(false, false, true);
-            break;
-
-        case 2:
-            OCC(false, true, false);
-            break;
-
-        case 3:
-            OCC(false, true, true);
-            break;
-
-        case 4:
-            OCC(true, false, false);
-            break;
-
-        case 5:
-            OCC(true, false, true);
-            break;
-
-        case 6:
-            OCC(true, true, false);
-            break;
-
-        default:
-            OCC(true, true, true);
-            break;
+    if (e == cudaSuccess) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, block, smem);
     }
 
-#undef OCC
     return (int)e;
 }
 

@@ -46,7 +46,8 @@ struct __attribute__((aligned(32))) mmcb_tetrec {
 // Havel / Plucker tetrahedron record (256 bytes): the per-face / per-edge tables of tracer_build
 // (src/mmc_mesh.c:1518-1567) followed by neighbours, node ids, type and flags.
 struct __attribute__((aligned(32))) mmcb_tetrec_big {
-    float tab[48];        // Havel: 4 faces x {n̂(4), e1(4), e2(4)}; Plucker: d[6][4] then m[6][4]
+    float tab[48];        // Havel: 4 faces x {n^(4), e1(4), e2(4)} (tracer_build, src/mmc_mesh.c:1532-1567);
+                          // Plucker: d[6][3], m[6][3] (:1518-1531) then the BLB face normals nx[4] ny[4] nz[4] for reflectray
     int   nb[4];          // facenb permuted to tracer face order
     int   node[4];        // element node ids (1-based)
     int   type;
@@ -58,6 +59,7 @@ struct mmcb_kparam {
     // source
     float srcpos[4], srcdir[4], srcparam1[4], srcparam2[4];
     int   srctype, srcnum, srcelemlen, e0;
+    float bary0[4];              // barycentric coordinates of srcpos in e0 (cfg->bary0; nodal Havel/Plucker deposit)
     float focus;
     // time gates
     float tstart, tend, Rtstep;

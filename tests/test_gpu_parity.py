@@ -134,6 +134,50 @@ def test_energy_conservation_and_deposit_completeness(mesh):
     assert abs(g["raw"].sum() / g["energyabs"][0] - 1) < 2e-4
 
 
+HP_CASES = ["havel_elem", "havel_nodal", "plucker_elem", "plucker_nodal"]
+
+
+@pytest.mark.parametrize("name", HP_CASES)
+def test_havel_plucker_parity_vs_oracle(name, mesh):
+    """Havel and Plucker exist only in the reference's CPU file (src/mmc_raytrace.c:227-508,531-800): the oracle runs with
+    CPU semantics (gpu_semantics=0) and the CUDA kernels must reproduce its absorbed fraction, work per photon and
+    per-gate / per-node (or per-element) fluence within Monte Carlo noise."""
+    node, elem, et, med = mesh
+    kw = cases.case_kwargs(name)
+    N = 200000
+    kw["nphoton"] = N
+    o = orc.run(node, elem, et, med, nthread=8, gpu_semantics=0, **kw)
+    g = mmc.run(_cfg(node, elem, et, med, **kw))
+    fo = (o["absorbweight"] / o["launchweight"])[0]
+    fg = g["energyabs"][0] / g["energytot"][0]
+    sigma = np.sqrt(max(fo * (1 - fo), 1e-4) / N)
+    assert abs(fg - fo) < 6 * sigma + 3e-4, (fg, fo, sigma)
+    assert abs(g["raytet"] / o["raytet"] - 1) < 0.02
+    fo_, fg_ = o["field"][..., 0], g["raw"][..., 0]
+    assert fo_.shape == fg_.shape
+    go, gg = fo_.sum(axis=1), fg_.sum(axis=1)
+    big = go > 0.02 * go.sum()
+    np.testing.assert_allclose(gg[big], go[big], rtol=0.03)
+    cw_o, cw_g = fo_.sum(axis=0), fg_.sum(axis=0)
+    lit = cw_o > 0.02 * cw_o.max()
+    rel = np.abs(cw_g[lit] - cw_o[lit]) / cw_o[lit]
+    assert np.median(rel) < 0.05, np.median(rel)
+    assert np.mean(rel) < 0.08, np.mean(rel)
+
+
+def test_three_tracers_agree_on_cube60():
+    """BASELINE config C1 with the tracer it names (Havel) and the two others: same absorbed fraction (reference CPU
+    anchors: Havel 17.70356 %, Plucker 17.69245 %, BL-Badouel 17.70358 % at 1e6 photons)."""
+    node, elem, et = mmc.meshgen.cube60()
+    med = [(0.005, 1.0, 0.01, 1.37)]
+    base = dict(nphoton=1000000, seed=1648335518, srcpos=(30.1, 30.2, 0.0), srcdir=(0, 0, 1), tstart=0.0, tend=5e-9,
+                tstep=1e-10, isreflect=0)
+    for method, anchor, steps in ((cases.HAVEL, 0.1770356, 206.9), (cases.PLUCKER, 0.1769245, 206.8), (cases.BLBADOUEL, 0.1770358, 206.9)):
+        g = mmc.run(_cfg(node, elem, et, med, method=method, **base))
+        assert abs(g["energyabs"][0] / g["energytot"][0] - anchor) < 2.5e-3, method
+        assert abs(g["raytet"] / 1e6 - steps) < 3.0, method
+
+
 @pytest.mark.parametrize("name", ["blb_energy", "grid_halfmm"])
 def test_hot_line_cache_loses_nothing(name, mesh):
     """The CTA-private sums for the hottest lines (pilot batch -> key table -> shared-memory accumulation -> flush) must
