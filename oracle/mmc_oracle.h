@@ -4,7 +4,7 @@
  * and bench.py's cpu_baseline leg as the CHECKER for the CUDA path.  It is never
  * linked into, imported by or called from the product library (mmc_b200/).
  *
- * Parity status: PINNED.  tests/test_oracle_vs_ref.py runs this restatement and the
+ * Parity status: PINNED.  tests/test_oracle_pin.py runs this restatement and the
  * unmodified reference binary (oracle/_ref/mmc_ref, built by oracle/Makefile.ref from
  * /root/reference/src) single-threaded on the same mesh/seed and requires the raw
  * fluence, energy tallies and detected-photon rows to agree; the resulting vectors are
