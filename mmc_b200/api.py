@@ -345,8 +345,36 @@ class _OutBuffers:
 
 
 def run(cfg):
-    """Run one simulation through the one-call C-ABI path (host buffers in, host buffers out) -- the
-    equivalent of pmmc.run(cfg) with cfg['compute']='cuda' (src/pmmc.cpp:1060-1075)."""
+    """Run one simulation, host buffers in, host buffers out -- the equivalent of pmmc.run(cfg) with cfg['compute']='cuda'
+    (src/pmmc.cpp:1060-1075).  Same work as the one-call mmcb_run_simulation (which the reference-side stub uses), spelled
+    with the session calls so that the output buffers are sized from the session instead of a second mesh preparation."""
+    prob = Problem(cfg)
+    L = lib()
+    h = L.mmcb_create(C.byref(prob.cfg), C.byref(prob.mesh), prob.device)
+    if not h:
+        raise MMCError(-1, L.mmcb_last_error().decode(errors="replace"))
+    try:
+        sz = Sizes()
+        _check(L.mmcb_get_sizes(h, C.byref(sz)))
+        buf = _OutBuffers(prob, sz)
+        respin = max(1, int(prob.cfg.respin))
+        n, per, ms = int(prob.cfg.nphoton), int(prob.cfg.nphoton) // respin, 0.0
+        t = C.c_float()
+        for it in range(respin):                      # src/mmc_cu_host.cu:656,893-906
+            cnt = per if it < respin - 1 else n - per * (respin - 1)
+            _check(L.mmcb_launch(h, cnt, per * it, int(prob.cfg.seed), it, None))
+            _check(L.mmcb_sync(h))
+            _check(L.mmcb_last_kernel_ms(h, C.byref(t)))
+            ms += t.value
+        _check(L.mmcb_fetch(h, None, None, C.byref(buf.out)))
+        buf.out.kernel_ms = ms
+    finally:
+        L.mmcb_destroy(h)
+    return buf.result(prob)
+
+
+def run_onecall(cfg):
+    """The same through the single C entry point mmcb_run_simulation (what integration/mmc_cu_host_b200.cpp calls)."""
     prob = Problem(cfg)
     sz = prob.sizes()
     buf = _OutBuffers(prob, sz)

@@ -764,6 +764,37 @@ void build_records_big(const PrepMesh& m, const Cfg& cfg, const std::vector<mmcb
     }
 }
 
+// Device memory comes from the stream-ordered pool (cudaMallocAsync): a session is ~25 buffers, and plain cudaFree costs up
+// to ~20 ms each next to another allocator's arena (measured: 390 ms to tear a session down inside the bench process).
+// The pool keeps the memory for the next session of the process.
+thread_local cudaStream_t g_stream = NULL;
+
+int pool_setup(int device) {
+    static bool done[64] = {false};
+
+    if (device >= 0 && device < 64 && !done[device]) {
+        cudaMemPool_t pool;
+        CU(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        done[device] = true;
+    }
+
+    return 0;
+}
+
+template <typename T>
+int dev_alloc(T** dptr, size_t n) {
+    CU(cudaMallocAsync((void**)dptr, n * sizeof(T), g_stream));
+    return 0;
+}
+
+void dev_free(void* p) {
+    if (p) {
+        cudaFreeAsync(p, g_stream);
+    }
+}
+
 template <typename T>
 int dev_alloc_copy(T** dptr, const T* host, size_t n) {
     *dptr = NULL;
@@ -772,12 +803,12 @@ int dev_alloc_copy(T** dptr, const T* host, size_t n) {
         return 0;
     }
 
-    CU(cudaMalloc((void**)dptr, n * sizeof(T)));
+    CU(cudaMallocAsync((void**)dptr, n * sizeof(T), g_stream));
 
-    if (host) {
-        CU(cudaMemcpy(*dptr, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    if (host) {     // pageable source: the runtime stages the bytes before returning, the vector may die afterwards
+        CU(cudaMemcpyAsync(*dptr, host, n * sizeof(T), cudaMemcpyHostToDevice, g_stream));
     } else {
-        CU(cudaMemset(*dptr, 0, n * sizeof(T)));
+        CU(cudaMemsetAsync(*dptr, 0, n * sizeof(T), g_stream));
     }
 
     return 0;
@@ -842,36 +873,41 @@ static int session_free(mmcb_session* s) {
     }
 
     cudaSetDevice(s->device);
-    cudaFree(s->d_tet);
-    cudaFree(s->d_tetbig);
-    cudaFree(s->d_cent);
-    cudaFree(s->d_node);
-    cudaFree(s->d_elem);
-    cudaFree(s->d_srcelem);
-    cudaFree(s->d_med);
-    cudaFree(s->d_pattern);
-    cudaFree(s->d_seeds);
-    cudaFree(s->d_replayseed);
-    cudaFree(s->d_replayweight);
-    cudaFree(s->d_replaytime);
+    g_stream = s->stream;
+    dev_free(s->d_tet);
+    dev_free(s->d_tetbig);
+    dev_free(s->d_cent);
+    dev_free(s->d_node);
+    dev_free(s->d_elem);
+    dev_free(s->d_srcelem);
+    dev_free(s->d_med);
+    dev_free(s->d_pattern);
+    dev_free(s->d_seeds);
+    dev_free(s->d_replayseed);
+    dev_free(s->d_replayweight);
+    dev_free(s->d_replaytime);
 
     if (!s->field_external) {
-        cudaFree(s->d_field);
+        dev_free(s->d_field);
     }
 
-    cudaFree(s->d_dref);
-    cudaFree(s->d_detected);
-    cudaFree(s->d_detcount);
-    cudaFree(s->d_detseed);
-    cudaFree(s->d_traj);
-    cudaFree(s->d_trajcount);
-    cudaFree(s->d_energy);
-    cudaFree(s->d_raytet);
-    cudaFree(s->d_counter);
-    cudaFree(s->d_hotkeys);
-    cudaFree(s->d_hotstat);
-    cudaFree(s->d_hotcand);
+    dev_free(s->d_dref);
+    dev_free(s->d_detected);
+    dev_free(s->d_detcount);
+    dev_free(s->d_detseed);
+    dev_free(s->d_traj);
+    dev_free(s->d_trajcount);
+    dev_free(s->d_energy);
+    dev_free(s->d_raytet);
+    dev_free(s->d_counter);
+    dev_free(s->d_hotkeys);
+    dev_free(s->d_hotstat);
+    dev_free(s->d_hotcand);
     delete s->seedgen;
+
+    if (s->stream) {
+        cudaStreamSynchronize(s->stream);
+    }
 
     if (s->ev0) {
         cudaEventDestroy(s->ev0);
@@ -918,6 +954,12 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     s->device = device;
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    g_stream = s->stream;
+
+    if (pool_setup(device)) {
+        return g_code;
+    }
+
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
     tr.mark("device+stream");
@@ -984,8 +1026,8 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
         return fail(MMCB_ERR_LIMIT, "output volume of %zu entries exceeds the 32-bit index range of the kernel", s->efieldlen);
     }
 
-    CU(cudaMalloc(&s->d_field, s->efieldlen * (s->acc_double ? 8 : 4)));
-    CU(cudaMemset(s->d_field, 0, s->efieldlen * (s->acc_double ? 8 : 4)));
+    CU(cudaMallocAsync(&s->d_field, s->efieldlen * (s->acc_double ? 8 : 4), s->stream));
+    CU(cudaMemsetAsync(s->d_field, 0, s->efieldlen * (s->acc_double ? 8 : 4), s->stream));
 
     if (c.issaveref) {
         if ((rc = dev_alloc_copy(&s->d_dref, (const double*)NULL, (size_t)m.nf * s->cfg.maxgate))) {
@@ -1047,8 +1089,9 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
 
     tr.mark("alloc+upload");
     // launch shape: persistent grid = resident CTAs per SM x SM count (the reference sizes to 64 thr x 32 x #SM, src/mmc_cu_host.cu:159-163)
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
+    int smcount = 0, smemoptin = 0;       // two attributes instead of cudaGetDeviceProperties (several ms per call)
+    CU(cudaDeviceGetAttribute(&smcount, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaDeviceGetAttribute(&smemoptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     s->block = (c.nblocksize > 0) ? c.nblocksize : 128;
     s->block = std::max(32, (s->block / 32) * 32);
     s->smem_base = sizeof(float4) * m.med.size() + (s->isdet ? sizeof(float) * (size_t)devreclen * s->block : 0);
@@ -1057,15 +1100,15 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     s->smem = s->smem_base + (s->hot_allowed ? sizeof(unsigned int) * MMCB_HOT_SLOTS + sizeof(float) * MMCB_HOT_SLOTS * MMCB_HOT_GROUP : 0);
 
     if (s->hot_allowed) {
-        CU(cudaMalloc(&s->d_hotkeys, sizeof(unsigned int) * MMCB_HOT_SLOTS));
-        CU(cudaMemset(s->d_hotkeys, 0xFF, sizeof(unsigned int) * MMCB_HOT_SLOTS));
-        CU(cudaMalloc(&s->d_hotstat, sizeof(unsigned int) * MMCB_HOT_STAT_WORDS));
-        CU(cudaMemset(s->d_hotstat, 0, sizeof(unsigned int) * MMCB_HOT_STAT_WORDS));
-        CU(cudaMalloc(&s->d_hotcand, sizeof(uint2) * 2 * MMCB_HOT_SLOTS));
+        CU(cudaMallocAsync(&s->d_hotkeys, sizeof(unsigned int) * MMCB_HOT_SLOTS, s->stream));
+        CU(cudaMemsetAsync(s->d_hotkeys, 0xFF, sizeof(unsigned int) * MMCB_HOT_SLOTS, s->stream));
+        CU(cudaMallocAsync(&s->d_hotstat, sizeof(unsigned int) * MMCB_HOT_STAT_WORDS, s->stream));
+        CU(cudaMemsetAsync(s->d_hotstat, 0, sizeof(unsigned int) * MMCB_HOT_STAT_WORDS, s->stream));
+        CU(cudaMallocAsync(&s->d_hotcand, sizeof(uint2) * 2 * MMCB_HOT_SLOTS, s->stream));
     }
 
-    if (s->smem > (size_t)prop.sharedMemPerBlockOptin) {
-        return fail(MMCB_ERR_LIMIT, "media table and detector records need %zu bytes of shared memory, device offers %zu", s->smem, (size_t)prop.sharedMemPerBlockOptin);
+    if (s->smem > (size_t)smemoptin) {
+        return fail(MMCB_ERR_LIMIT, "media table and detector records need %zu bytes of shared memory, device offers %zu", s->smem, (size_t)smemoptin);
     }
 
     int bps = 0;
@@ -1078,11 +1121,11 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     if (c.nthread > 0) {
         s->grid = std::max(1, c.nthread / s->block);
     } else {
-        s->grid = bps * prop.multiProcessorCount;
+        s->grid = bps * smcount;
     }
 
     s->nthread = s->grid * s->block;
-    CU(cudaMalloc(&s->d_seeds, sizeof(uint32_t) * 4 * (size_t)s->nthread));
+    CU(cudaMallocAsync(&s->d_seeds, sizeof(uint32_t) * 4 * (size_t)s->nthread, s->stream));
     // kernel parameters
     mmcb_kparam& k = s->kp;
     memset(&k, 0, sizeof(k));
@@ -1159,6 +1202,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     a.energy = s->d_energy;
     a.raytet = s->d_raytet;
     a.photon_counter = s->d_counter;
+    CU(cudaStreamSynchronize(s->stream));      // uploads done: launches may come on any stream
     tr.mark("occupancy+params");
     return 0;
 }
@@ -1339,7 +1383,7 @@ int mmcb_set_field_buffer(mmcb_session* s, void* device_ptr) {
     CU(cudaSetDevice(s->device));
 
     if (!s->field_external) {
-        cudaFree(s->d_field);
+        dev_free(s->d_field);
     }
 
     s->d_field = device_ptr;
@@ -1642,12 +1686,12 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
         const bool nodal = (!s->isgrid && !s->ishp && c.basisorder);
 
         if (nodal) {
-            CU(cudaMalloc(&d_tmp, sizeof(double) * s->fieldlen));
+            CU(cudaMallocAsync(&d_tmp, sizeof(double) * s->fieldlen, s->stream));
             CU(cudaMemsetAsync(d_tmp, 0, sizeof(double) * s->fieldlen, s->stream));
             CUK(mmcb_k_spread_nodes(s->d_field, d_tmp, s->d_elem, m.ne, m.nn, s->cfg.maxgate, c.srcnum, s->stream));
             CU(cudaMemcpyAsync(W.data(), d_tmp, sizeof(double) * s->fieldlen, cudaMemcpyDeviceToHost, s->stream));
         } else if (!s->acc_double) {
-            CU(cudaMalloc(&d_tmp, sizeof(double) * s->fieldlen));
+            CU(cudaMallocAsync(&d_tmp, sizeof(double) * s->fieldlen, s->stream));
             CUK(mmcb_k_acc_to_double(s->d_field, d_tmp, s->fieldlen, s->stream));
             CU(cudaMemcpyAsync(W.data(), d_tmp, sizeof(double) * s->fieldlen, cudaMemcpyDeviceToHost, s->stream));
         } else {
@@ -1657,7 +1701,7 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
         CU(cudaStreamSynchronize(s->stream));
 
         if (d_tmp) {
-            cudaFree(d_tmp);
+            cudaFreeAsync(d_tmp, s->stream);
         }
 
         tr.mark("fetch: volume D2H");

@@ -224,6 +224,19 @@ def test_full_size_cube60_anchor():
     assert abs(g1["raytet"] / 1e6 - 338.9) < 4.0
 
 
+def test_onecall_entry_point_matches_session_path(mesh):
+    """mmcb_run_simulation (the entry the reference-side stub calls) and create/launch/fetch/destroy are the same engine."""
+    node, elem, et, med = mesh
+    kw = cases.case_kwargs("blb_detectors")
+    kw["nphoton"] = 100000
+    a = mmc.run(_cfg(node, elem, et, med, **kw))
+    b = mmc.run_onecall(_cfg(node, elem, et, med, **kw))
+    assert a["energytot"][0] == b["energytot"][0] == kw["nphoton"]
+    assert abs(a["energyabs"][0] / b["energyabs"][0] - 1) < 0.01
+    assert abs(len(a["detp"]) - len(b["detp"])) < 6 * np.sqrt(len(a["detp"])) + 5
+    assert a["raw"].shape == b["raw"].shape
+
+
 def test_errors_match_reference_convention(mesh):
     node, elem, et, med = mesh
     kw = cases.case_kwargs("blb_elem_reflect")
