@@ -18,6 +18,26 @@ def two_media_cube(n=20, step=2):
     return node, elem, et, med
 
 
+def wide_slab():
+    """Small replaywide-style slab (examples/replaywide/createmesh.m:3-29): 20x20x10 mm of medium 1, air layers below
+    (tets labelled -1: wide-field source candidates) and above (-2: wide-field detector)."""
+    node, elem, et = meshgen.slab_with_wide_src_det(nx=20, ny=20, nz=10, step=2, gap=2.0)
+    med = [(0.01, 1.0, 0.01, 1.37)]
+    return node, elem, et, med
+
+
+MESHES = {"cube": two_media_cube, "slab": wide_slab}
+
+
+def case_mesh(name):
+    return MESHES[CASES[name].get("mesh", "cube")]()
+
+
+def _pattern(nx, ny, srcnum):
+    rs = np.random.RandomState(3)
+    return (rs.rand(ny * nx, srcnum) > 0.4).astype(np.float32).reshape(-1)
+
+
 BASE = dict(nphoton=3000, seed=1648335518, srcpos=(10.1, 10.2, 0.0), srcdir=(0.0, 0.0, 1.0),
             tstart=0.0, tend=5e-9, tstep=5e-10)
 
@@ -40,6 +60,16 @@ CASES = {
                           detpos=[(10, 8, 0, 1.5), (10, 12, 0, 1.5)], exact=True),
     "blb_isotropic": dict(method=BLBADOUEL, srctype=1, srcpos=(10.1, 10.2, 6.3), exact=False),
     "blb_mirror": dict(method=BLBADOUEL, isreflect=3, exact=True),
+    # wide-field sources / detector on the slab (BASELINE config C5 family)
+    "planar_widedet": dict(mesh="slab", method=BLBADOUEL, isreflect=1, srctype=4, srcpos=(5.0, 5.0, -1.0),
+                           srcparam1=(10.0, 0, 0, 0), srcparam2=(0, 10.0, 0, 0), issavedet=1, issaveexit=1, exact=True),
+    "pattern_share2": dict(mesh="slab", method=BLBADOUEL, isreflect=1, srctype=5, srcpos=(4.0, 4.0, -1.0),
+                           srcparam1=(12.0, 0, 0, 4), srcparam2=(0, 12.0, 0, 4), srcnum=2, srcpattern=_pattern(4, 4, 2), exact=True),
+    "disk_grid": dict(mesh="slab", method=GRID, steps=1.0, isreflect=1, srctype=8, srcpos=(10.0, 10.0, -1.0),
+                      srcparam1=(3.0, 0, 0, 0), exact=True),
+    "planar_havel_nodal": dict(mesh="slab", method=HAVEL, basisorder=1, isreflect=1, srctype=4, srcpos=(5.0, 5.0, -1.0),
+                               srcparam1=(10.0, 0, 0, 0), srcparam2=(0, 10.0, 0, 0), exact=False),
+    "blb_dref": dict(method=BLBADOUEL, isreflect=1, issaveref=1, exact=True),
 }
 
 
@@ -47,4 +77,5 @@ def case_kwargs(name):
     kw = dict(BASE)
     kw.update(CASES[name])
     kw.pop("exact")
+    kw.pop("mesh", None)
     return kw

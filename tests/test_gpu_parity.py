@@ -57,49 +57,69 @@ def test_rng_bit_exact_on_device():
 
 
 GPU_CASES = ["blb_elem_raw", "blb_elem_reflect", "grid_1mm", "grid_halfmm", "blb_onegate", "blb_fluence",
-             "blb_energy", "blb_detectors", "blb_isotropic", "blb_mirror"]
+             "blb_energy", "blb_detectors", "blb_isotropic", "blb_mirror", "planar_widedet", "pattern_share2", "disk_grid",
+             "blb_dref"]
+
+
+def _finite(a):
+    return np.where(np.isfinite(a), a, 0.0)        # void (mua = 0) elements normalise to inf/nan in the reference as well
 
 
 @pytest.mark.parametrize("name", GPU_CASES)
-def test_statistical_parity_vs_oracle(name, mesh):
-    node, elem, et, med = mesh
+def test_statistical_parity_vs_oracle(name):
+    node, elem, et, med = cases.case_mesh(name)
     kw = cases.case_kwargs(name)
     N = 200000 if name != "blb_mirror" else 20000
     kw["nphoton"] = N
     o = orc.run(node, elem, et, med, nthread=8, gpu_semantics=1, **kw)
     g = mmc.run(_cfg(node, elem, et, med, **kw))
-    # energy bookkeeping: launched, absorbed = tot - esc (src/mmc_cu_host.cu:988)
-    assert abs(g["energytot"][0] - o["launchweight"][0]) <= 1e-6 * N
-    fo = (o["launchweight"][0] - o["escweight"][0]) / o["launchweight"][0]
-    fg = g["energyabs"][0] / g["energytot"][0]
-    sigma = np.sqrt(max(fo * (1 - fo), 1e-4) / N)
-    assert abs(fg - fo) < 6 * sigma + 2e-4, (fg, fo, sigma)
+    srcnum = kw.get("srcnum", 1)
+    for k in range(srcnum):
+        # energy bookkeeping: launched, absorbed = tot - esc (src/mmc_cu_host.cu:988)
+        assert abs(g["energytot"][k] - o["launchweight"][k]) <= 2e-3 * N
+        fo = (o["launchweight"][k] - o["escweight"][k]) / o["launchweight"][k]
+        fg = g["energyabs"][k] / g["energytot"][k]
+        sigma = np.sqrt(max(fo * (1 - fo), 1e-4) / N)
+        assert abs(fg - fo) < 6 * sigma + 3e-4, (k, fg, fo, sigma)
+        # output volume: per-gate sums and the well-lit entries
+        fo_, fg_ = _finite(o["field"][..., k]), _finite(g["raw"][..., k])
+        assert fo_.shape == fg_.shape
+        assert np.array_equal(np.isfinite(o["field"][..., k]), np.isfinite(g["raw"][..., k]))
+        tot = fo_.sum()
+        go, gg = fo_.sum(axis=1), fg_.sum(axis=1)
+        big = go > 0.02 * tot
+        np.testing.assert_allclose(gg[big], go[big], rtol=0.03)
+        assert abs(fg_.sum() / tot - 1) < 0.02
+        cw_o, cw_g = fo_.sum(axis=0), fg_.sum(axis=0)
+        lit = cw_o > 0.02 * cw_o.max()
+        rel = np.abs(cw_g[lit] - cw_o[lit]) / cw_o[lit]
+        assert np.median(rel) < 0.05, np.median(rel)
+        assert np.mean(rel) < 0.08, np.mean(rel)
     # work per photon
     assert abs(g["raytet"] / o["raytet"] - 1) < 0.02
-    # output volume: per-gate sums and the well-lit entries
-    fo_, fg_ = o["field"][..., 0], g["raw"][..., 0]
-    assert fo_.shape == fg_.shape
-    tot = fo_.sum()
-    go, gg = fo_.sum(axis=1), fg_.sum(axis=1)
-    big = go > 0.02 * tot
-    np.testing.assert_allclose(gg[big], go[big], rtol=0.03)
-    assert abs(fg_.sum() / tot - 1) < 0.02
-    cw_o, cw_g = fo_.sum(axis=0), fg_.sum(axis=0)
-    lit = cw_o > 0.02 * cw_o.max()
-    rel = np.abs(cw_g[lit] - cw_o[lit]) / cw_o[lit]
-    assert np.median(rel) < 0.05, np.median(rel)
-    assert np.mean(rel) < 0.08, np.mean(rel)
+    if kw.get("issaveref"):                         # diffuse reflectance per exterior face and gate (-X 1)
+        do, dg = o["dref"], g["dref"]
+        assert do.shape == dg.shape
+        assert abs(dg.sum() / do.sum() - 1) < 0.02
+        hot = do.sum(axis=0) > 0.05 * do.sum(axis=0).max()
+        np.testing.assert_allclose(dg.sum(axis=0)[hot], do.sum(axis=0)[hot], rtol=0.15)
     if kw.get("issavedet"):
         no, ng = o["detectedcount"], len(g["detp"])
         assert abs(no - ng) < 6 * np.sqrt(max(no, 1)) + 5, (no, ng)
         assert g["detp"].shape[1] == o["reclen"]
         # columns: detid, nscat[M], ppath[M], mom[M], p[3], v[3], w0
-        do, dg = o["detected"], g["detp"]
-        for col in (0, 3, 4):                      # detector id mix, partial paths
+        do, dg = o["detected"][:no], g["detp"]
+        M = len(med)
+        for col in (1, 1 + M):                      # scattering counts and partial paths of medium 1
             assert abs(do[:, col].mean() - dg[:, col].mean()) < 0.1 * max(abs(do[:, col].mean()), 0.05)
         vn = np.linalg.norm(dg[:, -4:-1], axis=1)
         assert np.allclose(vn, 1.0, atol=1e-4)     # exit directions are unit vectors (examples/regression/exitangle)
-        assert np.all(dg[:, -5] <= 1e-3)           # exit z on the z=0 face where the detectors sit
+        if name == "blb_detectors":
+            assert abs(do[:, 0].mean() - dg[:, 0].mean()) < 0.1            # detector id mix
+            assert np.all(dg[:, -5] <= 1e-3)       # exit z on the z=0 face where the detectors sit
+        else:                                      # wide-field detector: rows are taken where photons leave the detector layer
+            assert abs(do[:, -5].mean() - dg[:, -5].mean()) < 0.1
+            assert (dg[:, -5] > 10.0 - 1e-3).mean() > 0.95
 
 
 def test_per_photon_seed_parity(mesh):
@@ -134,15 +154,15 @@ def test_energy_conservation_and_deposit_completeness(mesh):
     assert abs(g["raw"].sum() / g["energyabs"][0] - 1) < 2e-4
 
 
-HP_CASES = ["havel_elem", "havel_nodal", "plucker_elem", "plucker_nodal"]
+HP_CASES = ["havel_elem", "havel_nodal", "plucker_elem", "plucker_nodal", "planar_havel_nodal"]
 
 
 @pytest.mark.parametrize("name", HP_CASES)
-def test_havel_plucker_parity_vs_oracle(name, mesh):
+def test_havel_plucker_parity_vs_oracle(name):
     """Havel and Plucker exist only in the reference's CPU file (src/mmc_raytrace.c:227-508,531-800): the oracle runs with
     CPU semantics (gpu_semantics=0) and the CUDA kernels must reproduce its absorbed fraction, work per photon and
     per-gate / per-node (or per-element) fluence within Monte Carlo noise."""
-    node, elem, et, med = mesh
+    node, elem, et, med = cases.case_mesh(name)
     kw = cases.case_kwargs(name)
     N = 200000
     kw["nphoton"] = N

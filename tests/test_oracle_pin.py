@@ -27,13 +27,15 @@ def mesh():
 
 
 @pytest.mark.parametrize("name", list(cases.CASES))
-def test_oracle_matches_golden(name, gold, mesh):
+def test_oracle_matches_golden(name, gold):
     z, meta = gold
-    node, elem, et, med = mesh
+    node, elem, et, med = cases.case_mesh(name)
     o = orc.run(node, elem, et, med, **cases.case_kwargs(name))
     f = o["field"].reshape(-1)
     m = meta[name]
     assert f.size == m["size"]
+    assert int((~np.isfinite(f)).sum()) == m.get("nonfinite", 0)     # void elements: 0/0 in mesh_normalize, as in the reference
+    f = np.where(np.isfinite(f), f, 0.0)
     exact = cases.CASES[name]["exact"]
     rtol = 1e-9 if exact else 5e-3
     if exact:
@@ -53,22 +55,23 @@ def test_oracle_matches_golden(name, gold, mesh):
     if m["absorbed_frac"] is not None:
         frac = (o["absorbweight"] / o["launchweight"])[0]
         assert abs(frac - m["absorbed_frac"]) < (2e-7 if exact else 5e-3)
-    if m["normalizer"] is not None:
+    if m["normalizer"] is not None and cases.CASES[name].get("srcnum", 1) == 1:   # the log prints one normalizor per pattern
         assert abs(o["normalizer"] / m["normalizer"] - 1) < (1e-5 if exact else 1e-2)
     if m["detectedcount"] is not None:
         assert o["detectedcount"] == m["detectedcount"]
 
 
 @pytest.mark.skipif(not orc.ref_available(), reason="oracle/_ref/mmc_ref not built (needs /root/reference)")
-@pytest.mark.parametrize("name", ["blb_elem_reflect", "grid_halfmm", "plucker_nodal", "havel_nodal", "blb_detectors"])
-def test_oracle_matches_reference_binary(name, mesh):
-    node, elem, et, med = mesh
+@pytest.mark.parametrize("name", ["blb_elem_reflect", "grid_halfmm", "plucker_nodal", "havel_nodal", "blb_detectors",
+                                  "planar_widedet", "pattern_share2", "disk_grid"])
+def test_oracle_matches_reference_binary(name):
+    node, elem, et, med = cases.case_mesh(name)
     kw = cases.case_kwargs(name)
     o = orc.run(node, elem, et, med, **kw)
     r = orc.run_ref(node, elem, et, med, nthread=1, **kw)
     a, f = o["field"].reshape(-1), r["field_flat"]
     if cases.CASES[name]["exact"]:
-        assert np.array_equal(a, f), "oracle is not bit-identical to the reference at 1 thread"
+        assert np.array_equal(a, f, equal_nan=True), "oracle is not bit-identical to the reference at 1 thread"
         assert o["raytet"] == r["raytet"]
     else:
         assert np.abs(a - f).max() <= 1e-3 * f.max()

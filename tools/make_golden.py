@@ -25,13 +25,15 @@ def sample_idx(n, k=64):
 
 
 def main():
-    node, elem, et, med = cases.two_media_cube()
     out = {}
     meta = {}
     for name in cases.CASES:
+        node, elem, et, med = cases.case_mesh(name)
         kw = cases.case_kwargs(name)
         r = orc.run_ref(node, elem, et, med, nthread=1, **kw)
         f = r["field_flat"]
+        nonfinite = int((~np.isfinite(f)).sum())       # void (mua=0) elements normalise to inf/nan in the reference itself
+        f = np.where(np.isfinite(f), f, 0.0)
         idx = np.argsort(-f)[:32]                      # the 32 largest entries ...
         idx = np.unique(np.concatenate([idx, sample_idx(len(f))]))   # ... plus 64 random ones
         out[name + "/idx"] = idx.astype(np.int64)
@@ -40,7 +42,7 @@ def main():
         out[name + "/gatesum"] = f.reshape(ng, -1).sum(axis=1)
         meta[name] = dict(raytet=r.get("raytet"), absorbed_frac=r.get("absorbed_frac"),
                           normalizer=r.get("normalizer"), detectedcount=r.get("detectedcount"),
-                          total=float(f.sum()), size=int(len(f)))
+                          total=float(f.sum()), size=int(len(f)), nonfinite=nonfinite)
         print(name, meta[name])
     out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_cases.npz"), **out)
