@@ -929,7 +929,11 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                     }
 
                     if (!GENERAL || gp.srcnum == 1) {
-                        etot += p.w;
+                        if (HP && GENERAL && gp.isreplay && (gp.outputtype == 4 || gp.outputtype == 5)) {
+                            etot += a.replayweight[p.id];       // CPU-file semantics: src/mmc_raytrace.c:1811-1816
+                        } else {
+                            etot += p.w;
+                        }
                     } else {
                         for (int k = 0; k < gp.srcnum; k++) {
                             red_add_d(a.energy + k, (double)(p.w * a.srcpattern[(size_t)p.posidx * gp.srcnum + k]));

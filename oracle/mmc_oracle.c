@@ -1802,7 +1802,9 @@ static int onephoton(uint64_t id, octx* c, uint64_t* ran) {
     if (cfg->srctype != stPattern || cfg->srcnum == 1) {
         r.partialpath[c->reclen - 2] = r.weight;
 
-        if (cfg->seed == ORC_SEED_FROM_FILE && (cfg->outputtype == ORC_WL || cfg->outputtype == ORC_WP)) {
+        /* CPU: the launched "energy" of a wl/wp replay is the detected weight (src/mmc_raytrace.c:1811-1816); the CUDA
+         * kernel adds r.weight = 1 for every photon (src/mmc_core.cl:1907-1908) */
+        if (cfg->seed == ORC_SEED_FROM_FILE && (cfg->outputtype == ORC_WL || cfg->outputtype == ORC_WP) && !cfg->gpu_semantics) {
             kahany = cfg->replayweight[r.photonid] - c->kahanc0[0];
         } else {
             kahany = r.weight - c->kahanc0[0];

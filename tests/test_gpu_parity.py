@@ -145,6 +145,40 @@ def test_per_photon_seed_parity(mesh):
     assert abs(g["raw"].sum() / o["field"].sum() - 1) < 5e-3
 
 
+@pytest.mark.parametrize("otype", ["wl", "wp", "jacobian", "wl-havel"])
+def test_replay_outputs_vs_oracle(otype, tmp_path):
+    """BASELINE config C5 flow (examples/replaywide): run 1 saves detected photons + seeds (.mch), run 2 replays them
+    (-E file.mch -O L|P|J) and accumulates path lengths / scattering counts weighted by the detected weight.  Replayed
+    photons carry their own seeds, so GPU and oracle follow the same trajectories up to fp rounding."""
+    from mmc_b200 import mch
+    node, elem, et, med = cases.case_mesh("planar_widedet")
+    kw = cases.case_kwargs("planar_widedet")
+    kw.update(nphoton=60000, issaveseed=1)
+    first = mmc.run(_cfg(node, elem, et, med, **kw))
+    assert len(first["detp"]) > 3000
+    f = str(tmp_path / "init.mch")
+    mch.savemch(f, first["detp"], first["seeds"], maxmedia=len(med), totalphoton=kw["nphoton"], normalizer=first["normalizer"])
+    rp = mch.replay_inputs(mch.loadmch(f), np.vstack([[0, 0, 1, 1], med]))
+    n = rp["nphoton"]
+    kw2 = {k: v for k, v in kw.items() if k not in ("seed", "nphoton", "issaveseed")}
+    kw2.update(outputtype={"wl": cases.WL, "wp": cases.WP, "jacobian": cases.JACOBIAN, "wl-havel": cases.WL}[otype], minenergy=0.0)
+    if otype == "wl-havel":
+        kw2["method"] = cases.HAVEL
+    o = orc.run(node, elem, et, med, nthread=8, gpu_semantics=0 if otype == "wl-havel" else 1, seed=orc.SEED_FROM_FILE, nphoton=n, photonseed=rp["replayseed"],
+                replayweight=rp["replayweight"], replaytime=rp["replaytime"], **kw2)
+    cfg = _cfg(node, elem, et, med, **kw2)
+    cfg.update(replayseed=rp["replayseed"], replayweight=rp["replayweight"], replaytime=rp["replaytime"])
+    g = mmc.run(cfg)
+    # replay invariant of the reference (matlab/mmcjmua.m:55-60): the replayed photons are detected again, same rows
+    assert abs(len(g["detp"]) - n) <= 0.02 * n
+    fo, fg = np.where(np.isfinite(o["field"][..., 0]), o["field"][..., 0], 0), np.where(np.isfinite(g["raw"][..., 0]), g["raw"][..., 0], 0)
+    assert abs(fg.sum() / fo.sum() - 1) < 5e-3
+    cw_o, cw_g = fo.sum(axis=0), fg.sum(axis=0)
+    lit = cw_o > 0.05 * cw_o.max()
+    rel = np.abs(cw_g[lit] - cw_o[lit]) / cw_o[lit]
+    assert np.median(rel) < 0.02 and np.percentile(rel, 95) < 0.1, (np.median(rel), np.percentile(rel, 95))
+
+
 def test_energy_conservation_and_deposit_completeness(mesh):
     """sum(raw energy deposits) == launched - escaped: no deposit is lost between the merged-run flushes."""
     node, elem, et, med = mesh
