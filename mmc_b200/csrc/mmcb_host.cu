@@ -1007,8 +1007,21 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
         return rc;
     }
 
-    if ((rc = dev_alloc_copy((mmcb_medium**)&s->d_med, m.med.data(), m.med.size()))) {
-        return rc;
+    {
+        // device media table: two float4 per medium -- {mua, mus, g, n} and the per-step derived constants
+        // {1/mus (0: no scattering), n/c0, 1/mua (0: mua < EPS), c0/n} so that the step issues no divisions for them
+        std::vector<float4> dm(2 * m.med.size());
+
+        for (size_t i = 0; i < m.med.size(); i++) {
+            const mmcb_medium& q = m.med[i];
+            const float rc = q.n * 3.335640951981520e-12f;
+            dm[2 * i] = make_float4(q.mua, q.mus, q.g, q.n);
+            dm[2 * i + 1] = make_float4(q.mus <= 1e-6f ? 0.f : 1.f / q.mus, rc, q.mua < 1e-6f ? 0.f : 1.f / q.mua, 1.f / rc);
+        }
+
+        if ((rc = dev_alloc_copy(&s->d_med, dm.data(), dm.size()))) {
+            return rc;
+        }
     }
 
     if ((rc = dev_alloc_copy(&s->d_pattern, s->cfg.pattern.data(), s->cfg.pattern.size()))) {
@@ -1094,7 +1107,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     CU(cudaDeviceGetAttribute(&smemoptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     s->block = (c.nblocksize > 0) ? c.nblocksize : 128;
     s->block = std::max(32, (s->block / 32) * 32);
-    s->smem_base = sizeof(float4) * m.med.size() + (s->isdet ? sizeof(float) * (size_t)devreclen * s->block : 0);
+    s->smem_base = 2 * sizeof(float4) * m.med.size() + (s->isdet ? sizeof(float) * (size_t)devreclen * s->block : 0);
     s->hot_allowed = (c.hotcache >= 0 && srcnum == 1);
     // the grid (= number of RNG streams) is sized for the larger footprint so that pilot and main launch share it
     s->smem = s->smem_base + (s->hot_allowed ? sizeof(unsigned int) * MMCB_HOT_SLOTS + sizeof(float) * MMCB_HOT_SLOTS * MMCB_HOT_GROUP : 0);
@@ -1154,6 +1167,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     k.roulettesize = c.roulettesize;
     k.nout = c.nout;
     k.doroulette = ((c.tend - c.tstart) * k.Rtstep <= 1.f);
+    k.roulette_w = (k.doroulette && c.minenergy > 0.f) ? c.minenergy : -1.f;
     k.nn = m.nn;
     k.ne = m.ne;
     k.nf = m.nf;

@@ -30,6 +30,7 @@ typedef MMCB_ACC_T acc_t;
 #define R_MIN_MUS       1e9f
 #define FIX_PHOTON      1e-3f
 #define TWO_PI_D        (3.14159265358979323846 * 2.0)   // src/mmc_mesh.h:69: a double expression
+#define TWO_PI_F        6.28318530717958647692f
 #define JUST_BELOW_ONE  0.9998f
 #define DELTA_MUA       1e-4f
 #define POOL_CHUNK      32
@@ -126,7 +127,9 @@ __device__ __forceinline__ void rotatevector(float& vx, float& vy, float& vz, fl
 // mc_next_scatter, src/mmc_core.cl:1344-1377
 __device__ __forceinline__ float next_scatter(float g, Photon& p, Rng& rng, float& mom) {
     float nextslen = rand_scatlen(rng);
-    float tmp0 = (float)(TWO_PI_D * rand01(rng));
+    // the reference multiplies by the double expression TWO_PI (src/mmc_mesh.h:69) and rounds to float; the float product
+    // differs from that by at most one ulp of the angle and saves two conversions and a DMUL per scattering event
+    float tmp0 = TWO_PI_F * rand01(rng);
     float sphi, cphi, stheta, ctheta;
     sincosf(tmp0, &sphi, &cphi);
 
@@ -383,7 +386,7 @@ __device__ __forceinline__ void reflectray(Photon& p, int& neweid, float nx, flo
 
     if (neweid > 0) {
         int t2 = a.tet[neweid - 1].type;         // rare path: one extra 4-byte gather
-        n2 = smed[t2].w;
+        n2 = smed[2 * t2].w;
     }
 
     float tmp0 = n1 * n1, tmp1 = n2 * n2;
@@ -654,7 +657,7 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
     }
 
     flags = ((unsigned)tf.y) >> fi;
-    prop = smed[type];
+    prop = smed[2 * type];
     const float mus = prop.y;
     const float dlen = (mus <= EPS) ? R_MIN_MUS : p.slen / mus;
     isend = (Lp0 > dlen);
@@ -791,14 +794,14 @@ mmcb_photon_kernel(const mmcb_kargs a) {
     unsigned int* hkeys = (unsigned int*)smem4;
     float* hvals = (float*)smem4 + MMCB_HOT_SLOTS;
     float4* smed = smem4 + (gp.hotcache ? MMCB_HOT_BYTES / 16 : 0);     // media table, gp.nmedia entries
-    float* ppath = (float*)(smed + gp.nmedia);                  // DET: [reclen][blockDim]
+    float* ppath = (float*)(smed + 2 * gp.nmedia);                  // DET: [reclen][blockDim]
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xFFFFFFFFu;
     acc_t* field = (acc_t*)a.field;
     const unsigned long long gfield = (unsigned long long)__cvta_generic_to_global(a.field);
 
-    for (int i = threadIdx.x; i < gp.nmedia; i += blockDim.x) {
+    for (int i = threadIdx.x; i < 2 * gp.nmedia; i += blockDim.x) {      // {mua mus g n}, {1/mus n/c0 1/mua c0/n} per medium
         smed[i] = a.med[i];
     }
 
@@ -845,114 +848,116 @@ mmcb_photon_kernel(const mmcb_kargs a) {
 
     while (true) {
         // ------------------------------------------------------------------ photon supply
-        unsigned need = __ballot_sync(FULL, state == 0);
+        if (!__all_sync(FULL, state == 1)) {       // some lane is out of work: one vote per iteration in the steady state
+            unsigned need = __ballot_sync(FULL, state == 0);
 
-        if (need) {
-            unsigned int myid = 0;
-            bool got = false;
+            if (need) {
+                unsigned int myid = 0;
+                bool got = false;
 
-            if (gp.schedule == 1) {
-                if (state == 0 && pool_next < pool_end) {
-                    myid = pool_next++;
-                    got = true;
+                if (gp.schedule == 1) {
+                    if (state == 0 && pool_next < pool_end) {
+                        myid = pool_next++;
+                        got = true;
+                    }
+                } else {
+                    const int n = __popc(need);
+                    unsigned int base = 0;
+                    int avail = 0;
+
+                    if (lane == 0 && pool_end - pool_next < (unsigned int)n) {
+                        // serve what is left of the old range first (base/avail), then open a fresh chunk
+                        base = pool_next;
+                        avail = (int)(pool_end - pool_next);
+                        const unsigned int want = (unsigned int)(POOL_CHUNK + n - avail);
+                        const unsigned long long g0 = atom_add_u64(a.photon_counter, want);
+                        pool_next = (unsigned int)min(g0, (unsigned long long)nlaunch);
+                        pool_end = max((unsigned int)min(g0 + want, (unsigned long long)nlaunch), pool_next);
+                    }
+
+                    // broadcast the pool and distribute: first `avail` needy lanes take the leftover range, the rest the pool
+                    avail = __shfl_sync(FULL, avail, 0);
+                    base = __shfl_sync(FULL, base, 0);
+                    const unsigned int pn = __shfl_sync(FULL, pool_next, 0);
+                    const unsigned int pe = __shfl_sync(FULL, pool_end, 0);
+                    const int rank = __popc(need & ((1u << lane) - 1));
+
+                    if (state == 0) {
+                        if (rank < avail) {
+                            myid = base + rank;
+                            got = true;
+                        } else {
+                            const unsigned int cand = pn + (unsigned int)(rank - avail);
+
+                            if (cand < pe) {
+                                myid = cand;
+                                got = true;
+                            }
+                        }
+                    }
+
+                    if (lane == 0) {
+                        pool_next = min(pool_next + (unsigned int)max(0, n - avail), pool_end);
+                    }
                 }
-            } else {
-                const int n = __popc(need);
-                unsigned int base = 0;
-                int avail = 0;
-
-                if (lane == 0 && pool_end - pool_next < (unsigned int)n) {
-                    // serve what is left of the old range first (base/avail), then open a fresh chunk
-                    base = pool_next;
-                    avail = (int)(pool_end - pool_next);
-                    const unsigned int want = (unsigned int)(POOL_CHUNK + n - avail);
-                    const unsigned long long g0 = atom_add_u64(a.photon_counter, want);
-                    pool_next = (unsigned int)min(g0, (unsigned long long)nlaunch);
-                    pool_end = max((unsigned int)min(g0 + want, (unsigned long long)nlaunch), pool_next);
-                }
-
-                // broadcast the pool and distribute: first `avail` needy lanes take the leftover range, the rest the pool
-                avail = __shfl_sync(FULL, avail, 0);
-                base = __shfl_sync(FULL, base, 0);
-                const unsigned int pn = __shfl_sync(FULL, pool_next, 0);
-                const unsigned int pe = __shfl_sync(FULL, pool_end, 0);
-                const int rank = __popc(need & ((1u << lane) - 1));
 
                 if (state == 0) {
-                    if (rank < avail) {
-                        myid = base + rank;
-                        got = true;
-                    } else {
-                        const unsigned int cand = pn + (unsigned int)(rank - avail);
+                    if (got) {
+                        p.id = myid + (unsigned int)gp.photon_offset;
 
-                        if (cand < pe) {
-                            myid = cand;
-                            got = true;
+                        if (GENERAL && gp.isreplay) {           // src/mmc_core.cl:2191-2194
+                            rng.t0 = a.replayseed[2 * (size_t)p.id];
+                            rng.t1 = a.replayseed[2 * (size_t)p.id + 1];
                         }
-                    }
-                }
 
-                if (lane == 0) {
-                    pool_next = min(pool_next + (unsigned int)max(0, n - avail), pool_end);
+                        if (DET) {
+                            initseed = rng;
+
+                            for (int k = 0; k < reclen; k++) {
+                                PPATH(k) = 0.f;
+                            }
+                        }
+
+                        launch_photon<GENERAL>(p, rng, a);
+
+                        if constexpr (HP) {
+                            bary0 = launch_bary(p, a);
+                        }
+
+                        if (DET) {
+                            if (!GENERAL || gp.srctype != 5 || gp.srcnum == 1) {
+                                PPATH(reclen - 1) = p.w;                       // :1894-1898
+                            } else {
+                                PPATH(reclen - 1) = __uint_as_float(p.posidx);
+                            }
+                        }
+
+                        if (!GENERAL || gp.srcnum == 1) {
+                            if (HP && GENERAL && gp.isreplay && (gp.outputtype == 4 || gp.outputtype == 5)) {
+                                etot += a.replayweight[p.id];       // CPU-file semantics: src/mmc_raytrace.c:1811-1816
+                            } else {
+                                etot += p.w;
+                            }
+                        } else {
+                            for (int k = 0; k < gp.srcnum; k++) {
+                                red_add_d(a.energy + k, (double)(p.w * a.srcpattern[(size_t)p.posidx * gp.srcnum + k]));
+                            }
+                        }
+
+                        if (GENERAL && gp.savetraj) {
+                            savedebug(p, a);
+                        }
+
+                        state = 1;
+                    } else {
+                        state = 2;
+                    }
                 }
             }
 
-            if (state == 0) {
-                if (got) {
-                    p.id = myid + (unsigned int)gp.photon_offset;
-
-                    if (GENERAL && gp.isreplay) {           // src/mmc_core.cl:2191-2194
-                        rng.t0 = a.replayseed[2 * (size_t)p.id];
-                        rng.t1 = a.replayseed[2 * (size_t)p.id + 1];
-                    }
-
-                    if (DET) {
-                        initseed = rng;
-
-                        for (int k = 0; k < reclen; k++) {
-                            PPATH(k) = 0.f;
-                        }
-                    }
-
-                    launch_photon<GENERAL>(p, rng, a);
-
-                    if constexpr (HP) {
-                        bary0 = launch_bary(p, a);
-                    }
-
-                    if (DET) {
-                        if (!GENERAL || gp.srctype != 5 || gp.srcnum == 1) {
-                            PPATH(reclen - 1) = p.w;                       // :1894-1898
-                        } else {
-                            PPATH(reclen - 1) = __uint_as_float(p.posidx);
-                        }
-                    }
-
-                    if (!GENERAL || gp.srcnum == 1) {
-                        if (HP && GENERAL && gp.isreplay && (gp.outputtype == 4 || gp.outputtype == 5)) {
-                            etot += a.replayweight[p.id];       // CPU-file semantics: src/mmc_raytrace.c:1811-1816
-                        } else {
-                            etot += p.w;
-                        }
-                    } else {
-                        for (int k = 0; k < gp.srcnum; k++) {
-                            red_add_d(a.energy + k, (double)(p.w * a.srcpattern[(size_t)p.posidx * gp.srcnum + k]));
-                        }
-                    }
-
-                    if (GENERAL && gp.savetraj) {
-                        savedebug(p, a);
-                    }
-
-                    state = 1;
-                } else {
-                    state = 2;
-                }
+            if (!__any_sync(FULL, state == 1)) {
+                break;
             }
-        }
-
-        if (__all_sync(FULL, state == 2)) {
-            break;
         }
 
         int detid = 0;
@@ -962,7 +967,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
         nraytet++;
         float Lmove = 0.f, fnx = 0.f, fny = 0.f, fnz = 0.f;
         float4 prop = make_float4(0.f, 0.f, 0.f, 1.f);
-        int neweid = 0, type = 0;
+        int neweid = 0, type = 0, faceidx = 0;
         unsigned flags = 0;
         bool found = false, isend = false, timeup = false;
         bool terminate = false, detect = false;
@@ -975,41 +980,39 @@ mmcb_photon_kernel(const mmcb_kargs a) {
         ld256((const char*)rec + 32, r1);                   // nz[4] d[4]
         ld256((const char*)rec + 64, r2);                   // nb[4] type flags
         // src/mmc_core.cl:752-771: T_j = (d_j - N_j.p) / (N_j.v) for faces with N_j.v > 0, else 1e10; the exit face is the first
-        // minimum.  The neighbour id and the outward normal of the running minimum are carried along, so the 24 record
-        // registers die here instead of living through the deposit code.
-        float Lmin = 1e10f;
-        int faceidx = 4;
+        // minimum.  Only the neighbour id is selected here; the outward normal is needed by reflectray alone (index-mismatch
+        // faces) and is re-read there from the record, which is an L1 hit, so the 24 record registers die before the deposit code.
+        float T[4];
         #pragma unroll
 
         for (int j = 0; j < 4; j++) {
             const float S = p.vx * r0[j] + p.vy * r0[4 + j] + p.vz * r1[j];
             const float Tn = r1[4 + j] - (p.px * r0[j] + p.py * r0[4 + j] + p.pz * r1[j]);
-            const float T = (S > 0.f) ? __fdividef(Tn, S) : 1e10f;
-
-            if (T < Lmin) {
-                Lmin = T;
-                faceidx = j;
-                neweid = __float_as_int(r2[j]);
-                fnx = r0[j];
-                fny = r0[4 + j];
-                fnz = r1[j];
-            }
+            T[j] = (S > 0.f) ? __fdividef(Tn, S) : 1e10f;
         }
 
+        const float Lmin = fminf(fminf(T[0], T[1]), fminf(T[2], T[3]));
+        faceidx = (T[0] == Lmin) ? 0 : ((T[1] == Lmin) ? 1 : ((T[2] == Lmin) ? 2 : 3));
+        neweid = __float_as_int((faceidx == 0) ? r2[0] : ((faceidx == 1) ? r2[1] : ((faceidx == 2) ? r2[2] : r2[3])));
         type = __float_as_int(r2[4]);
         flags = __float_as_uint(r2[5]) >> faceidx;      // bit 0: reflect, bit 4: to void, bit 8: from void
-        found = (faceidx < 4 && Lmin >= 0.f);
+        found = (Lmin < 1e10f && Lmin >= 0.f);
 
         if (found) {
-            prop = smed[type];                              // mua mus g n
-            Lmove = (prop.y <= EPS) ? R_MIN_MUS : __fdividef(p.slen, prop.y);
+            prop = smed[2 * type];                          // mua mus g n
+            const float4 pd = smed[2 * type + 1];           // 1/mus (0: none), n/c0, 1/mua (0: mua < EPS), c0/n
+            Lmove = (pd.x == 0.f) ? R_MIN_MUS : p.slen * pd.x;
             isend = (Lmin > Lmove);
             Lmove = isend ? Lmove : Lmin;
-            const float rc = prop.w * R_C0;
+            const float rc = pd.y;
+            float tnew = p.t + Lmove * rc;
+            int gate = (int)((tnew - gp.tstart) * gp.Rtstep);
 
-            if ((int)((p.t + Lmove * rc - gp.tstart) * gp.Rtstep) > gp.maxgate - 1) {   // :803-807
+            if (gate > gp.maxgate - 1) {                    // :803-807
                 timeup = true;
-                Lmove = (gp.tend - p.t) / rc - 1e-4f;
+                Lmove = (gp.tend - p.t) * pd.w - 1e-4f;
+                tnew = p.t + Lmove * rc;
+                gate = min((int)((tnew - gp.tstart) * gp.Rtstep), gp.maxgate - 1);
             }
 
             float currweight = p.w;
@@ -1027,19 +1030,16 @@ mmcb_photon_kernel(const mmcb_kargs a) {
 
             p.slen -= Lmove * prop.y;
             float ww = currweight - p.w;
-            p.t += Lmove * rc;
-            int gate;
+            p.t = tnew;
 
             if (GENERAL && (gp.outputtype == 4 || gp.outputtype == 5)) {
                 gate = min((int)(a.replaytime[p.id] * gp.Rtstep), gp.maxgate - 1);
-            } else {
-                gate = min((int)((p.t - gp.tstart) * gp.Rtstep), gp.maxgate - 1);
             }
 
             const unsigned int tshift = (unsigned int)gate * gp.framelen;
 
             if (gp.outputtype != 2 && gp.outputtype != 4 && gp.outputtype != 5) {       // :844-851
-                ww = (prop.x < EPS) ? (currweight * Lmove) : __fdividef(ww, prop.x);
+                ww = (pd.z == 0.f) ? (currweight * Lmove) : (ww * pd.z);
             }
 
             const bool flushnow = timeup || !isend;
@@ -1133,6 +1133,13 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 // ---- cross the face: neighbour hop + boundary physics :1950-1990
                 // r.p0 = r.pout: already there, Lmove == Lmin on this branch
                 if (gp.isreflect && (flags & 1u)) {
+                    if constexpr (!HP) {                    // outward normal of the exit face: record sectors 0/1, L1-resident
+                        const mmcb_tetrec* rec = a.tet + (p.eid - 1);
+                        fnx = __ldg(rec->nx + faceidx);
+                        fny = __ldg(rec->ny + faceidx);
+                        fnz = __ldg(rec->nz + faceidx);
+                    }
+
                     reflectray(p, neweid, fnx, fny, fnz, prop.w, smed, a, rng);
                 }
 
@@ -1157,7 +1164,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 // ---- end of the scattering path: roulette :2101-2114, then a new direction :2117-2135
                 bool dead = false;
 
-                if (gp.doroulette && gp.minenergy > 0.f && p.w < gp.minenergy) {
+                if (p.w < gp.roulette_w) {                  // roulette_w = minenergy when roulette applies, else -1
                     if (rand01(rng) * gp.roulettesize <= 1.f) {
                         p.w *= gp.roulettesize;
                     } else {

@@ -68,6 +68,7 @@ struct mmcb_kparam {
     int   isreflect, isspecular, voidtime, isextdet, outputtype, method, basisorder;
     float minenergy, roulettesize, nout;
     int   doroulette;            // (tend-tstart)*Rtstep <= 1 (src/mmc_core.cl:2101)
+    float roulette_w;            // minenergy when doroulette && minenergy > 0, else -1: `w < roulette_w` is the whole roulette test
     // mesh sizes
     int   nn, ne, nf, maxmedia;
     unsigned int framelen;       // per-gate stride of the accumulator volume
