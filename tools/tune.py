@@ -12,11 +12,10 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "build", "variants")
 VARIANTS = {
     "b128_m8": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=8"],
-    "b128_m9": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=9"],
-    "b128_m10": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=10"],
-    "b128_m7": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=7"],
-    "b128_m8_h7": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=8", "-DMMCB_HOT_SLOTS_LOG2=7"],
-    "b128_m8_h6": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=8", "-DMMCB_HOT_SLOTS_LOG2=6"],
+    "b128_m8_pf": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=8", "-DMMCB_PREFETCH"],
+    "b128_m6": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=6"],
+    "b128_m6_pf": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=6", "-DMMCB_PREFETCH"],
+    "b256_m4": ["-DMMCB_MAXTHREADS=256", "-DMMCB_MINBLOCKS=4"],
 }
 
 
@@ -39,7 +38,7 @@ def main():
             continue
         block = tag.split("_")[0][1:]
         for w in wl:
-            for hot in ((-1, 0) if tag == "b128_m8" else (0,)):
+            for hot in (0,):
                 name, method, nph = w.split(":")
                 env = dict(os.environ, MMCB_LIB=lib, MMCB_BLOCK=block, MMCB_HOTCACHE=str(hot))
                 r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", name, "--method", method, "--photons", nph,
