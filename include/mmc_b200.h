@@ -40,7 +40,11 @@ extern "C" {
 /* ray tracers, src/mmc_utils.h enum TRTMethod ('-M p|h|b|s|g') */
 enum { MMCB_RT_PLUCKER = 0, MMCB_RT_HAVEL = 1, MMCB_RT_BADOUEL = 2, MMCB_RT_BLBADOUEL = 3, MMCB_RT_BLBADOUEL_GRID = 4 };
 /* output types, enum TOutputType ('-O X|F|E|J|L|P') */
-enum { MMCB_OT_FLUX = 0, MMCB_OT_FLUENCE = 1, MMCB_OT_ENERGY = 2, MMCB_OT_JACOBIAN = 3, MMCB_OT_WL = 4, MMCB_OT_WP = 5 };
+enum { MMCB_OT_FLUX = 0, MMCB_OT_FLUENCE = 1, MMCB_OT_ENERGY = 2, MMCB_OT_JACOBIAN = 3, MMCB_OT_WL = 4, MMCB_OT_WP = 5,
+       /* '-O R|A|D|W' (src/mmc_utils.h:106-111): RF forward and the adjoint Jacobians computed from a multi-slot run */
+       MMCB_OT_RF = 6, MMCB_OT_RFMUS = 7, MMCB_OT_ADJOINT = 8, MMCB_OT_ADJOINT_DCOEFF = 9, MMCB_OT_ADJOINT_MUS = 10,
+       MMCB_OT_ADJOINT_MUSP = 11, MMCB_OT_ADJOINT_MUAD = 12, MMCB_OT_ADJOINT_MUAMUSP = 13
+     };
 /* boundary conditions, enum TBoundary ('-b 0|1|2|3') */
 enum { MMCB_BC_NOREFLECT = 0, MMCB_BC_REFLECT = 1, MMCB_BC_ABSORB_EXTERIOR = 2, MMCB_BC_MIRROR = 3 };
 /* source types, src/mmc_const.h:49-62 */
@@ -111,6 +115,15 @@ typedef struct mmcb_config {
     int   respin;                /* repeat count, results accumulate (-r) */
     int   hotcache;              /* CTA-private sums for the hottest 128-byte lines of the volume, picked from a pilot batch:
                                     0 = auto (on from 500 000 photons per launch), 1 = always, -1 = never */
+    /* multi-slot sources / adjoint mode and RF forward (src/mmc_utils.h:144-152,240,275,303-311; src/mmc_core.cl:1431-1515) */
+    float omega;                 /* modulation angular frequency (rad/s); > 0 (and no replay) => complex (RF) fluence */
+    int   srcid;                 /* 0 default; -1 all slots of srcdata, one field block per slot; -2 append detectors as sources
+                                    without Jacobian output; > 0 only slot srcid-1 (cfg->srcid) */
+    int   extrasrclen;           /* entries of srcdata (cfg->extrasrclen) */
+    const float* srcdata;        /* extrasrclen*16 floats, ExtraSrc: srcpos(w = launch weight), srcdir(w = focal length), srcparam1
+                                    (x = disk radius), srcparam2 (w = enclosing element, filled by the library when 0) */
+    const float* detdir;         /* detnum*4 detector normals (w = focal length): needed to turn detectors into adjoint sources */
+    int   adjointmode;           /* mesh-mode J_mua: 0 full FEM form, 1 nodal approximation (cfg->adjointmode) */
 } mmcb_config;
 
 typedef struct mmcb_gpuinfo {    /* src/mmc_utils.h:187-201 GPUInfo */
@@ -139,12 +152,18 @@ typedef struct mmcb_output {
     double normalizer;           /* cfg->his.normalizer */
     float  kernel_ms;            /* CUDA-event time of the photon kernel(s) */
     int    e0;
+    double* field_im;            /* RF forward: imaginary part of the fluence, same layout as `field` (cfg->exportadjoint); may be NULL */
+    float*  jacob;               /* adjoint output types: sizes.jacoblen floats (cfg->exportjacob), layout [datalen][Ns*Nd] per component:
+                                    CW [J1] | CW dual [J1, J2] | RF [Re J1, Im J1] | RF dual [Re J1, Re J2, Im J1, Im J2]; may be NULL */
 } mmcb_output;
 
 typedef struct mmcb_sizes {
     int maxgate, datalen, reclen, nf, srcnum;
     int dim[3];                  /* dual-grid dimensions (cfg->dim) */
-    size_t fieldlen;             /* datalen*maxgate*srcnum */
+    size_t fieldlen;             /* datalen*maxgate*srcnum*nslots */
+    int nslots;                  /* field blocks: extrasrclen in multi-slot mode (srcid < 0), else 1; block stride datalen*maxgate */
+    int adj_ns, adj_nd;          /* adjoint output: source and detector slots */
+    size_t jacoblen;             /* floats in mmcb_output.jacob (0 unless an adjoint output type is requested) */
 } mmcb_sizes;
 
 typedef struct mmcb_session mmcb_session;

@@ -196,6 +196,13 @@ extern "C" void mmc_run_cu(mcconfig* cfg, tetmesh* mesh, raytracer* tracer) {
     c.nthread = cfg->autopilot ? 0 : cfg->nthread;
     c.nblocksize = cfg->autopilot ? 0 : cfg->nblocksize;
     c.respin = cfg->respin;
+    // multi-slot sources (built by mcx_prep + mesh_init_srcdata_eid in the caller, src/mmc_host.c:136-165), RF, adjoint output
+    c.omega = cfg->omega;
+    c.srcid = cfg->srcid;
+    c.extrasrclen = cfg->extrasrclen;
+    c.srcdata = (const float*)cfg->srcdata;         // ExtraSrc = 4 x float4 (src/mmc_utils.h:147-152)
+    c.detdir = (const float*)cfg->detdir;
+    c.adjointmode = cfg->adjointmode;
 
     mmcb_sizes sz;
     B200_ASSERT(mmcb_query_sizes(&c, &m, &sz));
@@ -226,6 +233,28 @@ extern "C" void mmc_run_cu(mcconfig* cfg, tetmesh* mesh, raytracer* tracer) {
         out.traj = cfg->exportdebugdata;
     }
 
+    // RF imaginary fluence (cfg->exportadjoint, float) and adjoint Jacobian (cfg->exportjacob), src/mmc_cu_host.cu:345-353,1203-1242
+    const bool isrf = (cfg->omega > 0.f && cfg->seed != SEED_FROM_FILE);
+    std::vector<double> field_im;
+
+    if (isrf) {
+        field_im.assign(sz.fieldlen, 0.0);
+        out.field_im = field_im.data();
+
+        if (cfg->exportadjoint == NULL) {
+            cfg->exportadjoint = (float*)calloc(sz.fieldlen, sizeof(float));
+        }
+    }
+
+    if (sz.jacoblen) {
+        if (cfg->exportjacob) {
+            free(cfg->exportjacob);
+        }
+
+        cfg->exportjacob = (float*)calloc(sz.jacoblen, sizeof(float));
+        out.jacob = cfg->exportjacob;
+    }
+
     MMC_FPRINTF(cfg->flog, "- code name: [MMC-B200] sm_100a photon engine (libmmc_b200 %x)\n", mmcb_version());
     MMC_FPRINTF(cfg->flog, "- [device %d(1): %s] np=%.1f maxgate=%d repetition=%d\n", gpuinfo[0].id, gpuinfo[0].name,
                 (double)cfg->nphoton, sz.maxgate, cfg->respin);
@@ -237,6 +266,10 @@ extern "C" void mmc_run_cu(mcconfig* cfg, tetmesh* mesh, raytracer* tracer) {
     unsigned int toc = GetTimeMillis() - tic;
     MMC_FPRINTF(cfg->flog, "kernel complete:  \t%d ms\nretrieving flux ... \t", (int)(out.kernel_ms + 0.5f));
     MMC_FPRINTF(cfg->flog, "transfer complete:        %d ms\n", toc);
+
+    for (size_t i = 0; i < field_im.size(); i++) {
+        cfg->exportadjoint[i] += (float)field_im[i];
+    }
 
     // ---- scalar results the callers read (src/mmc_cu_host.cu:757-759,775-782,823-853,995)
     cfg->runtime = (unsigned int)(out.kernel_ms + 0.5f);
@@ -286,6 +319,10 @@ extern "C" void mmc_run_cu(mcconfig* cfg, tetmesh* mesh, raytracer* tracer) {
 
     if (cfg->issaveref) {
         mesh_saveweight(mesh, cfg, 1);
+    }
+
+    if (cfg->issave2pt && cfg->parentid == mpStandalone && cfg->exportjacob && sz.jacoblen) {     // src/mmc_cu_host.cu:1244-1250,1385-1391
+        mesh_savejacob(cfg, mesh, cfg->exportjacob, sz.adj_ns, sz.adj_nd, isrf ? 1 : 0, MCX_IS_DUAL_ADJOINT_TYPE(cfg->outputtype));
     }
 
 #endif

@@ -25,7 +25,10 @@ SRCTYPES = ["pencil", "isotropic", "cone", "gaussian", "planar", "pattern", "fou
 METHODS = {"plucker": 0, "p": 0, "havel": 1, "h": 1, "badouel": 2, "b": 2, "elem": 3, "s": 3, "blbadouel": 3,
            "grid": 4, "g": 4}
 OUTPUTTYPES = {"flux": 0, "x": 0, "fluence": 1, "f": 1, "energy": 2, "e": 2, "jacobian": 3, "j": 3,
-               "wl": 4, "l": 4, "wp": 5, "p": 5}
+               "wl": 4, "l": 4, "wp": 5, "p": 5,
+               # RF forward and adjoint Jacobians (src/mmc_utils.c:4444-4449)
+               "rf": 6, "r": 6, "adjoint": 8, "a": 8, "adjointd": 9, "d": 9, "adjointmus": 10, "u": 10, "adjointmusp": 11, "v": 11,
+               "adjointmuad": 12, "w": 12, "adjointmuamusp": 13, "q": 13}
 
 
 class MMCError(RuntimeError):
@@ -61,7 +64,9 @@ class Config(C.Structure):
                 ("detnum", C.c_int), ("detpos", C.c_void_p), ("maxdetphoton", C.c_uint),
                 ("photonseed", C.c_void_p), ("replayweight", C.c_void_p), ("replaytime", C.c_void_p),
                 ("savetraj", C.c_int), ("maxjumpdebug", C.c_uint),
-                ("nthread", C.c_int), ("nblocksize", C.c_int), ("schedule", C.c_int), ("respin", C.c_int), ("hotcache", C.c_int)]
+                ("nthread", C.c_int), ("nblocksize", C.c_int), ("schedule", C.c_int), ("respin", C.c_int), ("hotcache", C.c_int),
+                ("omega", C.c_float), ("srcid", C.c_int), ("extrasrclen", C.c_int), ("srcdata", C.c_void_p), ("detdir", C.c_void_p),
+                ("adjointmode", C.c_int)]
 
 
 class GpuInfo(C.Structure):
@@ -76,12 +81,14 @@ class Output(C.Structure):
                 ("traj", C.c_void_p),
                 ("detectedcount", C.c_uint), ("detectedtotal", C.c_uint), ("trajcount", C.c_uint),
                 ("energytot", C.c_double * 16), ("energyesc", C.c_double * 16),
-                ("raytet", C.c_double), ("normalizer", C.c_double), ("kernel_ms", C.c_float), ("e0", C.c_int)]
+                ("raytet", C.c_double), ("normalizer", C.c_double), ("kernel_ms", C.c_float), ("e0", C.c_int),
+                ("field_im", C.c_void_p), ("jacob", C.c_void_p)]
 
 
 class Sizes(C.Structure):
     _fields_ = [("maxgate", C.c_int), ("datalen", C.c_int), ("reclen", C.c_int), ("nf", C.c_int), ("srcnum", C.c_int),
-                ("dim", C.c_int * 3), ("fieldlen", C.c_size_t)]
+                ("dim", C.c_int * 3), ("fieldlen", C.c_size_t), ("nslots", C.c_int), ("adj_ns", C.c_int), ("adj_nd", C.c_int),
+                ("jacoblen", C.c_size_t)]
 
 
 class DevPtrs(C.Structure):
@@ -208,7 +215,8 @@ DEFAULTS = dict(nphoton=0, seed=0x623F9A9E, srcpos=(0, 0, 0), srcdir=(0, 0, 1, 0
                 outputtype="flux", roulettesize=10.0, minenergy=1e-6, nout=1.0, voidtime=1, unitinmm=1.0,
                 steps=(1.0, 1.0, 1.0), detpos=None, maxdetphoton=1000000, maxjumpdebug=10000000,
                 debuglevel="", nthread=0, nblocksize=0, schedule=0, respin=1, hotcache=0, gpuid=1,
-                replayseed=None, replayweight=None, replaytime=None)
+                replayseed=None, replayweight=None, replaytime=None,
+                omega=0.0, srcid=0, srcdata=None, detdir=None, adjointmode=0)
 
 
 class Problem:
@@ -283,6 +291,17 @@ class Problem:
             self.keep.append(det)
             c.detnum, c.detpos = len(det), det.ctypes.data
         c.savetraj = 1 if ("M" in str(p["debuglevel"]).upper()) else 0
+        c.omega, c.srcid, c.adjointmode = float(p["omega"]), int(p["srcid"]), int(p["adjointmode"])
+        if p["srcdata"] is not None:      # rows of 16 floats: srcpos(4) srcdir(4) srcparam1(4) srcparam2(4) (ExtraSrc, src/mmc_utils.h:147-152)
+            sd = np.ascontiguousarray(p["srcdata"], dtype=np.float32).reshape(-1, 16)
+            self.keep.append(sd)
+            c.extrasrclen, c.srcdata = len(sd), sd.ctypes.data
+        if p["detdir"] is not None:
+            dd = np.ascontiguousarray(p["detdir"], dtype=np.float32).reshape(-1, 4)
+            if dd.shape[0] != c.detnum:
+                raise MMCError(-2, "detdir needs one row (nx, ny, nz, focal length) per detector")
+            self.keep.append(dd)
+            c.detdir = dd.ctypes.data
         if p["replayseed"] is not None:
             rs = np.ascontiguousarray(p["replayseed"]).view(np.uint64).reshape(-1, 2)
             rw = np.ascontiguousarray(p["replayweight"], dtype=np.float32)
@@ -310,16 +329,22 @@ class _OutBuffers:
         self.detected = np.zeros((max(nd, 1), sz.reclen), dtype=np.float32)
         self.detseed = np.zeros((max(nd, 1), 2), dtype=np.uint64)
         self.traj = np.zeros((int(c.maxjumpdebug) if c.savetraj else 1, 6), dtype=np.float32)
+        self.field_im = np.zeros(sz.fieldlen, dtype=np.float64) if (c.omega > 0 and c.seed != SEED_FROM_FILE) else None
+        self.jacob = np.zeros(sz.jacoblen, dtype=np.float32) if sz.jacoblen else None
         o = Output()
         o.field = self.field.ctypes.data
         o.dref = self.dref.ctypes.data if self.dref is not None else None
         o.detected, o.detseed, o.traj = self.detected.ctypes.data, self.detseed.ctypes.data, self.traj.ctypes.data
+        o.field_im = self.field_im.ctypes.data if self.field_im is not None else None
+        o.jacob = self.jacob.ctypes.data if self.jacob is not None else None
         self.out = o
         self.sz = sz
 
     def result(self, prob):
         o, sz, c = self.out, self.sz, prob.cfg
         srcnum = sz.srcnum
+        if sz.nslots > 1:
+            return self._result_slots(prob)
         flux = self.field.reshape(sz.maxgate, sz.datalen, srcnum)
         if prob.cfg.method == 4:
             # grid output: x fastest (idx = iz*dim.y*dim.x + iy*dim.x + ix), gates last like pmmc's 'flux'
@@ -341,6 +366,26 @@ class _OutBuffers:
             res["traj"] = self.traj[:o.trajcount].copy()
         if self.dref is not None:
             res["dref"] = self.dref.reshape(sz.maxgate, sz.nf).copy()
+        if self.field_im is not None:
+            res["raw_im"] = self.field_im.reshape(sz.maxgate, sz.datalen, srcnum)
+        return res
+
+    def _result_slots(self, prob):
+        """Multi-slot (adjoint) run: one [maxgate, datalen] block per source slot (src/mmc_cu_host.cu:930-938); 'jacob' holds the
+        adjoint Jacobian components as [component, Ns*Nd, datalen] (component order: see mmcb_output.jacob)."""
+        o, sz, c = self.out, self.sz, prob.cfg
+        raw = self.field.reshape(sz.nslots, sz.maxgate, sz.datalen)
+        res = dict(raw=raw, flux=raw, nslots=sz.nslots, energytot=np.array(o.energytot[:1]), energyesc=np.array(o.energyesc[:1]),
+                   raytet=o.raytet, normalizer=o.normalizer, kernel_ms=o.kernel_ms, e0=o.e0, detectedtotal=o.detectedtotal,
+                   maxgate=sz.maxgate, datalen=sz.datalen, reclen=sz.reclen, nf=sz.nf, dim=tuple(sz.dim))
+        res["energyabs"] = res["energytot"] - res["energyesc"]
+        if self.field_im is not None:
+            res["raw_im"] = self.field_im.reshape(sz.nslots, sz.maxgate, sz.datalen)
+        if self.jacob is not None:
+            res["jacob"] = self.jacob.reshape(-1, sz.adj_ns * sz.adj_nd, sz.datalen)
+            res["adj_ns"], res["adj_nd"] = sz.adj_ns, sz.adj_nd
+        if c.issavedet:
+            res["detp"] = self.detected[:o.detectedcount].copy()
         return res
 
 

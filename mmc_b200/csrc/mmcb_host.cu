@@ -21,8 +21,17 @@
 
 // kernel-side launchers (mmcb_kernel.cu)
 extern "C" int mmcb_k_upload_param(const mmcb_kparam* hp, const float* det4, int detnum, cudaStream_t st);
-extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int method, int isdet, int isgeneral, cudaStream_t st);
-extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int* blocks_per_sm);
+extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int method, int isdet, int isgeneral, int isrf, cudaStream_t st);
+extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int* blocks_per_sm);
+// adjoint-Jacobian post-kernels (mmcb_adjoint.cu)
+extern "C" int mmcb_k_adj_cw(const float* field, float* cw, size_t N, int maxgate, int nslots, cudaStream_t st);
+extern "C" int mmcb_k_adj_mua(const float* cw_re, const float* cw_im, float* out, size_t N, int Ns, int Nd, float scale, cudaStream_t st);
+extern "C" int mmcb_k_adj_dcoeff(const float* cw_re, const float* cw_im, float* out, size_t N, int Ns, int Nd, unsigned int Nx, unsigned int Ny,
+                                 float scale, cudaStream_t st);
+extern "C" int mmcb_k_adj_mesh_full(const float* cw_re, const float* cw_im, const int* elem, const float* node, const float* evol, float* jmua,
+                                    float* jd, int ne, int nn, int Ns, int Nd, cudaStream_t st);
+extern "C" int mmcb_k_adj_mesh_nodal(const float* cw_re, const float* cw_im, const float* nvol, float* jmua, int nn, int Ns, int Nd,
+                                     cudaStream_t st);
 extern "C" int mmcb_k_spread_nodes(const void* efield, double* nfield, const int* elem, int ne, int nn, int maxgate, int srcnum, cudaStream_t st);
 extern "C" int mmcb_k_acc_to_double(const void* in, double* out, size_t n, cudaStream_t st);
 extern "C" int mmcb_k_acc_is_double(void);
@@ -312,6 +321,11 @@ struct Cfg {              // validated copy of mmcb_config
     unsigned int crop0[3] = {0, 0, 0};
     std::vector<float> pattern, detpos;
     float bary0[4] = {0.f, 0.f, 0.f, 0.f};     // cfg->bary0: barycentric coordinates of srcpos in e0
+    // multi-slot sources / RF / adjoint output
+    std::vector<float> srcdata;                // extrasrclen x 16 (ExtraSrc)
+    int nslots = 1, multisrc = 0, isrf = 0;
+    int adj_ns = 0, adj_nd = 0, adj_dual = 0;  // adjoint output: source slots, detector slots, two components
+    size_t jacoblen = 0;
 };
 
 int validate(const mmcb_config* in, const mmcb_mesh* mesh, Cfg& o) {
@@ -417,6 +431,90 @@ int validate(const mmcb_config* in, const mmcb_mesh* mesh, Cfg& o) {
 
     if (c.detnum > 0) {
         o.detpos.assign(c.detpos, c.detpos + 4 * (size_t)c.detnum);
+    }
+
+    // ---- RF forward and multi-slot sources (mcx_prep, src/mmc_utils.c:3724-3800; mmc_run_simulation, src/mmc_cu_host.cu:229-233,262-264)
+    o.isrf = (c.omega > 0.f && c.seed != MMCB_SEED_FROM_FILE);
+
+    if (o.isrf && c.method != MMCB_RT_BLBADOUEL && c.method != MMCB_RT_BLBADOUEL_GRID) {
+        return fail(MMCB_ERR_INPUT, "RF (omega > 0) forward runs need the branch-less Badouel tracer (s or g), like the reference GPU path");
+    }
+
+    if (o.isrf && c.srcnum > 1) {
+        return fail(MMCB_ERR_INPUT, "RF forward runs do not support photon sharing (srcnum > 1)");
+    }
+
+    const bool isadjoint = (c.outputtype >= MMCB_OT_ADJOINT);
+
+    if (c.extrasrclen < 0 || (c.extrasrclen > 0 && !c.srcdata)) {
+        return fail(MMCB_ERR_INPUT, "extrasrclen > 0 needs srcdata");
+    }
+
+    if (c.extrasrclen > 0) {
+        o.srcdata.assign(c.srcdata, c.srcdata + 16 * (size_t)c.extrasrclen);
+    } else if ((isadjoint || c.srcid == -2) && c.seed != MMCB_SEED_FROM_FILE && c.detnum > 0 && c.detdir) {
+        // detectors become reversed (adjoint) sources behind the forward source(s): srcdata[0..Ns-1] forward, [Ns..Ns+Nd-1] detectors
+        const int Ns = c.srcnum, Nd = c.detnum;
+        c.extrasrclen = Ns + Nd;
+        o.srcdata.assign(16 * (size_t)c.extrasrclen, 0.f);
+
+        for (int is = 0; is < Ns; is++) {
+            float* q = &o.srcdata[16 * (size_t)is];
+            memcpy(q, c.srcpos, 12);
+            q[3] = 1.f / Ns;
+            memcpy(q + 4, c.srcdir, 12);
+            memcpy(q + 8, c.srcparam1, 16);
+            memcpy(q + 12, c.srcparam2, 16);
+        }
+
+        for (int id = 0; id < Nd; id++) {
+            float* q = &o.srcdata[16 * (size_t)(Ns + id)];
+            memcpy(q, c.detpos + 4 * (size_t)id, 12);
+            q[3] = 1.f / Nd;
+            memcpy(q + 4, c.detdir + 4 * (size_t)id, 16);
+            q[8] = c.detpos[4 * (size_t)id + 3];      // detector radius: disk source
+        }
+
+        if (isadjoint) {
+            c.srcid = -1;
+        }
+    }
+
+    if (c.extrasrclen > 0 && c.srcid > c.extrasrclen) {
+        return fail(MMCB_ERR_INPUT, "srcid exceeds total defined source count");
+    }
+
+    if (c.extrasrclen > 0 && c.srcid == 0) {
+        c.srcid = -1;          // srcdata without a selector: all slots (src/mmc_cu_host.cu:262)
+    }
+
+    o.multisrc = (c.extrasrclen > 0 && c.srcid != 0);
+    o.nslots = (c.extrasrclen > 0 && c.srcid < 0) ? c.extrasrclen : 1;
+
+    if (o.multisrc && c.srcnum > 1) {
+        return fail(MMCB_ERR_INPUT, "multi-slot sources (srcdata) cannot be combined with photon sharing (srcnum > 1)");
+    }
+
+    if (o.multisrc && c.seed == MMCB_SEED_FROM_FILE) {
+        return fail(MMCB_ERR_INPUT, "multi-slot sources are not supported under replay mode");
+    }
+
+    if (isadjoint) {
+        if (c.method != MMCB_RT_BLBADOUEL && c.method != MMCB_RT_BLBADOUEL_GRID) {
+            return fail(MMCB_ERR_INPUT, "adjoint Jacobian output needs the branch-less Badouel tracer (s or g)");
+        }
+
+        if (c.method != MMCB_RT_BLBADOUEL_GRID && !c.basisorder) {      // src/mmc_utils.c:3685-3690
+            return fail(MMCB_ERR_INPUT, "mesh-mode adjoint Jacobian requires basisorder=1 (nodal fluence)");
+        }
+
+        if (o.nslots < 2 || c.detnum < 1 || !c.detdir || c.extrasrclen <= c.detnum) {
+            return fail(MMCB_ERR_INPUT, "adjoint Jacobian output needs detectors with detdir and at least one source slot");
+        }
+
+        o.adj_nd = c.detnum;
+        o.adj_ns = c.extrasrclen - c.detnum;
+        o.adj_dual = (c.outputtype >= MMCB_OT_ADJOINT_MUAD);
     }
 
     return 0;
@@ -846,6 +944,8 @@ struct mmcb_session {
     unsigned long long* d_replayseed = NULL;
     float* d_replayweight = NULL, *d_replaytime = NULL;
     void* d_field = NULL;
+    void* d_field_im = NULL;       // RF: imaginary part
+    float4* d_srcdata = NULL;      // multi-slot sources
     double* d_dref = NULL;
     float* d_detected = NULL;
     unsigned int* d_detcount = NULL;
@@ -891,6 +991,8 @@ static int session_free(mmcb_session* s) {
         dev_free(s->d_field);
     }
 
+    dev_free(s->d_field_im);
+    dev_free(s->d_srcdata);
     dev_free(s->d_dref);
     dev_free(s->d_detected);
     dev_free(s->d_detcount);
@@ -970,7 +1072,24 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     s->ishp = (c.method == MMCB_RT_PLUCKER || c.method == MMCB_RT_HAVEL);
     s->isdet = c.issavedet != 0;
     s->isgeneral = !(c.srctype == MMCB_SRC_PENCIL || c.srctype == MMCB_SRC_ISOTROPIC) || c.srcnum > 1 ||
-                   c.seed == MMCB_SEED_FROM_FILE || c.savetraj || c.issaveref;
+                   c.seed == MMCB_SEED_FROM_FILE || c.savetraj || c.issaveref || s->cfg.multisrc || s->cfg.isrf;
+
+    // per-slot launch element (mesh_init_srcdata_eid, src/mmc_mesh.c:1114-1156): srcparam2.w of every slot that has none
+    for (int slot = 0; slot < c.extrasrclen; slot++) {
+        float* q = &s->cfg.srcdata[16 * (size_t)slot];
+
+        if (!(q[15] > 0.f)) {
+            float bary[4];
+            const int eid = initelem(m.node.data(), m.elem.data(), m.ne, q, bary);
+
+            if (eid <= 0 && c.srcid <= 0) {
+                return fail(MMCB_ERR_MESH, "source slot %d at (%g, %g, %g) is not enclosed by any element", slot + 1, q[0], q[1], q[2]);
+            }
+
+            q[15] = (float)std::max(eid, 0);
+        }
+    }
+
     // tables
     std::vector<mmcb_tetrec> rec;
     std::vector<float> cent;
@@ -1030,10 +1149,11 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
 
     // accumulators
     const int srcnum = c.srcnum;
-    s->fieldlen = (size_t)s->cfg.datalen * s->cfg.maxgate * srcnum;
+    const int nslots = s->cfg.nslots;
+    s->fieldlen = (size_t)s->cfg.datalen * s->cfg.maxgate * srcnum * nslots;
     // BLB deposits per element (nodal output is spread on fetch); Havel/Plucker deposit straight into nodes for basisorder=1
     size_t framelen = s->isgrid ? (size_t)s->cfg.crop0[2] : ((s->ishp && c.basisorder) ? (size_t)m.nn : (size_t)m.ne);
-    s->efieldlen = framelen * s->cfg.maxgate * srcnum;
+    s->efieldlen = framelen * s->cfg.maxgate * srcnum * nslots;
 
     if (s->efieldlen >= 0xFFFFFFFFull) {
         return fail(MMCB_ERR_LIMIT, "output volume of %zu entries exceeds the 32-bit index range of the kernel", s->efieldlen);
@@ -1041,6 +1161,15 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
 
     CU(cudaMallocAsync(&s->d_field, s->efieldlen * (s->acc_double ? 8 : 4), s->stream));
     CU(cudaMemsetAsync(s->d_field, 0, s->efieldlen * (s->acc_double ? 8 : 4), s->stream));
+
+    if (s->cfg.isrf) {
+        CU(cudaMallocAsync(&s->d_field_im, s->efieldlen * (s->acc_double ? 8 : 4), s->stream));
+        CU(cudaMemsetAsync(s->d_field_im, 0, s->efieldlen * (s->acc_double ? 8 : 4), s->stream));
+    }
+
+    if (c.extrasrclen > 0 && (rc = dev_alloc_copy((float**)&s->d_srcdata, s->cfg.srcdata.data(), s->cfg.srcdata.size()))) {
+        return rc;
+    }
 
     if (c.issaveref) {
         if ((rc = dev_alloc_copy(&s->d_dref, (const double*)NULL, (size_t)m.nf * s->cfg.maxgate))) {
@@ -1125,7 +1254,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     }
 
     int bps = 0;
-    CUK(mmcb_k_occupancy(s->block, s->smem, c.method, s->isdet, s->isgeneral, &bps));
+    CUK(mmcb_k_occupancy(s->block, s->smem, c.method, s->isdet, s->isgeneral, s->cfg.isrf, &bps));
 
     if (bps < 1) {
         return fail(MMCB_ERR_CUDA, "kernel cannot be resident with block=%d smem=%zu", s->block, s->smem);
@@ -1190,6 +1319,11 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     k.schedule = c.schedule;
     k.nmedia = (int)m.med.size();
     k.fieldlen = (unsigned int)s->efieldlen;
+    k.multisrc = s->cfg.multisrc;
+    k.srcid = c.srcid;
+    k.extrasrclen = c.extrasrclen;
+    k.slotstride = (unsigned int)(framelen * s->cfg.maxgate);
+    k.omega = s->cfg.isrf ? c.omega : 0.f;
     mmcb_kargs& a = s->ka;
     memset(&a, 0, sizeof(a));
     a.tet = s->d_tet;
@@ -1207,6 +1341,8 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     a.replayweight = s->d_replayweight;
     a.replaytime = s->d_replaytime;
     a.field = s->d_field;
+    a.field_im = s->d_field_im;
+    a.srcdata = s->d_srcdata;
     a.dref = s->d_dref;
     a.detected = s->d_detected;
     a.detcount = s->d_detcount;
@@ -1333,6 +1469,21 @@ int mmcb_mesh_initelem(int nn, const float* node, int ne, const int* elem, const
     return e0;
 }
 
+static void fill_sizes(const Cfg& c, int nf, mmcb_sizes* sz) {
+    sz->maxgate = c.maxgate;
+    sz->datalen = c.datalen;
+    sz->reclen = c.reclen;
+    sz->nf = nf;
+    sz->srcnum = c.c.srcnum;
+    memcpy(sz->dim, c.dim, sizeof(sz->dim));
+    sz->nslots = c.nslots;
+    sz->fieldlen = (size_t)c.datalen * c.maxgate * c.c.srcnum * c.nslots;
+    sz->adj_ns = c.adj_ns;
+    sz->adj_nd = c.adj_nd;
+    // [datalen][Ns*Nd] per component; RF doubles (Re, Im), dual types double again (src/mmc_cu_host.cu:1085-1094,1256-1263)
+    sz->jacoblen = (size_t)c.datalen * c.adj_ns * c.adj_nd * (c.isrf ? 2 : 1) * (c.adj_dual ? 2 : 1);
+}
+
 int mmcb_query_sizes(const mmcb_config* cfg, const mmcb_mesh* mesh, mmcb_sizes* sz) {
     Cfg c;
     PrepMesh m;
@@ -1346,13 +1497,7 @@ int mmcb_query_sizes(const mmcb_config* cfg, const mmcb_mesh* mesh, mmcb_sizes* 
         return rc;
     }
 
-    sz->maxgate = c.maxgate;
-    sz->datalen = c.datalen;
-    sz->reclen = c.reclen;
-    sz->nf = m.nf;
-    sz->srcnum = c.c.srcnum;
-    memcpy(sz->dim, c.dim, sizeof(sz->dim));
-    sz->fieldlen = (size_t)c.datalen * c.maxgate * c.c.srcnum;
+    fill_sizes(c, m.nf, sz);
     return 0;
 }
 
@@ -1379,13 +1524,7 @@ int mmcb_get_sizes(mmcb_session* s, mmcb_sizes* sz) {
         return fail(MMCB_ERR_INPUT, "null argument");
     }
 
-    sz->maxgate = s->cfg.maxgate;
-    sz->datalen = s->cfg.datalen;
-    sz->reclen = s->cfg.reclen;
-    sz->nf = s->mesh.nf;
-    sz->srcnum = s->cfg.c.srcnum;
-    memcpy(sz->dim, s->cfg.dim, sizeof(sz->dim));
-    sz->fieldlen = s->fieldlen;
+    fill_sizes(s->cfg, s->mesh.nf, sz);
     return 0;
 }
 
@@ -1463,7 +1602,7 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
         kp.hotcache = (part == 1 && s->hot_ready) ? 1 : 0;
         CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
         CUK(mmcb_k_upload_param(&kp, s->cfg.detpos.data(), c.detnum, st));
-        CUK(mmcb_k_launch_photons(&s->ka, s->grid, s->block, kp.hotcache ? s->smem : s->smem_base, c.method, s->isdet, s->isgeneral, st));
+        CUK(mmcb_k_launch_photons(&s->ka, s->grid, s->block, kp.hotcache ? s->smem : s->smem_base, c.method, s->isdet, s->isgeneral, s->cfg.isrf, st));
 
         if (part == 0) {     // the streams continue from the states the pilot wrote back (no reseeding)
             CUK(mmcb_k_hot_select(s->d_field, s->efieldlen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys,
@@ -1526,6 +1665,11 @@ int mmcb_reset(mmcb_session* s) {
 
     CU(cudaSetDevice(s->device));
     CU(cudaMemsetAsync(s->d_field, 0, s->efieldlen * (s->acc_double ? 8 : 4), s->stream));
+
+    if (s->d_field_im) {
+        CU(cudaMemsetAsync(s->d_field_im, 0, s->efieldlen * (s->acc_double ? 8 : 4), s->stream));
+    }
+
     CU(cudaMemsetAsync(s->d_energy, 0, sizeof(double) * 2 * MMCB_MAX_SRCNUM, s->stream));
     CU(cudaMemsetAsync(s->d_raytet, 0, sizeof(double), s->stream));
     CU(cudaMemsetAsync(s->d_detcount, 0, sizeof(unsigned int), s->stream));
@@ -1540,8 +1684,23 @@ int mmcb_reset(mmcb_session* s) {
     return 0;
 }
 
+static int rc_dev_alloc_float(float** d, const std::vector<float>& h, cudaStream_t st) {
+    cudaError_t e = cudaMallocAsync(d, sizeof(float) * h.size(), st);
+
+    if (e == cudaSuccess) {
+        e = cudaMemcpyAsync(*d, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice, st);
+    }
+
+    if (e != cudaSuccess) {
+        return fail(MMCB_ERR_CUDA, "%s", cudaGetErrorString(e));
+    }
+
+    return 0;
+}
+
 // mesh_normalize, src/mmc_mesh.c:2154-2279, on the host copy of the volume
-static double normalize_field(const mmcb_session* s, double* W, double* dref, float Eabsorb, float Etotal, int pair) {
+static double normalize_field(const mmcb_session* s, double* W, double* Wim, double* dref, float Eabsorb, float Etotal, int pair) {
+    // Wim: RF imaginary volume of this source slot (mesh_normalize's imag_slot, src/mmc_mesh.c:2204-2206) or NULL
     const mmcb_config& c = s->cfg.c;
     const PrepMesh& m = s->mesh;
     const int datalen = s->cfg.datalen, maxgate = s->cfg.maxgate, srcnum = c.srcnum;
@@ -1588,6 +1747,10 @@ static double normalize_field(const mmcb_session* s, double* W, double* dref, fl
             for (int j = 0; j < datalen; j++)
                 if (m.nvol[j] > 0.f) {
                     W[((size_t)i * datalen + j)*srcnum + pair] /= m.nvol[j];
+
+                    if (Wim) {
+                        Wim[(size_t)i * datalen + j] /= m.nvol[j];
+                    }
                 }
 
         for (int i = 0; i < m.ne; i++) {
@@ -1597,7 +1760,13 @@ static double normalize_field(const mmcb_session* s, double* W, double* dref, fl
             for (int j = 0; j < maxgate; j++)
                 for (int k = 0; k < 4; k++) {
                     float re_val = W[((size_t)j * m.nn + ee[k] - 1) * srcnum + pair];
-                    energyelem += re_val;
+
+                    if (Wim) {          // RF: |phi| (:2232-2237)
+                        float im_val = Wim[(size_t)j * m.nn + ee[k] - 1];
+                        energyelem += sqrtf(re_val * re_val + im_val * im_val);
+                    } else {
+                        energyelem += re_val;
+                    }
                 }
 
             energydeposit += energyelem * m.evol[i] * m.med[m.type[i]].mua;
@@ -1615,6 +1784,10 @@ static double normalize_field(const mmcb_session* s, double* W, double* dref, fl
 
             for (int j = 0; j < maxgate; j++) {
                 W[((size_t)j * datalen + i) * srcnum + pair] /= energyelem;
+
+                if (Wim) {      // the reference leaves the imaginary part undivided here (:2250-2256), which cannot be intended:
+                    Wim[(size_t)j * datalen + i] /= energyelem;     // both parts of one complex fluence get the same factor
+                }
             }
         }
 
@@ -1628,6 +1801,10 @@ static double normalize_field(const mmcb_session* s, double* W, double* dref, fl
     for (int i = 0; i < maxgate; i++)
         for (int j = 0; j < datalen; j++) {
             W[((size_t)i * datalen + j)*srcnum + pair] *= normalizor;
+
+            if (Wim) {
+                Wim[(size_t)i * datalen + j] *= (float)normalizor;
+            }
         }
 
     return normalizor;
@@ -1694,28 +1871,43 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
     }
 
     if (out->field) {
-        // raw sums -> double on the device (and elem->node spreading for nodal output), then one D2H copy
-        std::vector<double> W(s->fieldlen);
-        double* d_tmp = NULL;
+        // raw sums -> double on the device (and elem->node spreading for nodal output), then one D2H copy per volume
         const bool nodal = (!s->isgrid && !s->ishp && c.basisorder);
+        const int nslots = s->cfg.nslots;
+        auto download = [&](const void* d_src, std::vector<double>& W) -> int {
+            double* d_tmp = NULL;
+            W.resize(s->fieldlen);
 
-        if (nodal) {
-            CU(cudaMallocAsync(&d_tmp, sizeof(double) * s->fieldlen, s->stream));
-            CU(cudaMemsetAsync(d_tmp, 0, sizeof(double) * s->fieldlen, s->stream));
-            CUK(mmcb_k_spread_nodes(s->d_field, d_tmp, s->d_elem, m.ne, m.nn, s->cfg.maxgate, c.srcnum, s->stream));
-            CU(cudaMemcpyAsync(W.data(), d_tmp, sizeof(double) * s->fieldlen, cudaMemcpyDeviceToHost, s->stream));
-        } else if (!s->acc_double) {
-            CU(cudaMallocAsync(&d_tmp, sizeof(double) * s->fieldlen, s->stream));
-            CUK(mmcb_k_acc_to_double(s->d_field, d_tmp, s->fieldlen, s->stream));
-            CU(cudaMemcpyAsync(W.data(), d_tmp, sizeof(double) * s->fieldlen, cudaMemcpyDeviceToHost, s->stream));
-        } else {
-            CU(cudaMemcpyAsync(W.data(), s->d_field, sizeof(double) * s->fieldlen, cudaMemcpyDeviceToHost, s->stream));
+            if (nodal) {        // slot blocks are consecutive gate blocks of the same stride: maxgate*nslots "gates"
+                CU(cudaMallocAsync(&d_tmp, sizeof(double) * s->fieldlen, s->stream));
+                CU(cudaMemsetAsync(d_tmp, 0, sizeof(double) * s->fieldlen, s->stream));
+                CUK(mmcb_k_spread_nodes(d_src, d_tmp, s->d_elem, m.ne, m.nn, s->cfg.maxgate * nslots, c.srcnum, s->stream));
+                CU(cudaMemcpyAsync(W.data(), d_tmp, sizeof(double) * s->fieldlen, cudaMemcpyDeviceToHost, s->stream));
+            } else if (!s->acc_double) {
+                CU(cudaMallocAsync(&d_tmp, sizeof(double) * s->fieldlen, s->stream));
+                CUK(mmcb_k_acc_to_double(d_src, d_tmp, s->fieldlen, s->stream));
+                CU(cudaMemcpyAsync(W.data(), d_tmp, sizeof(double) * s->fieldlen, cudaMemcpyDeviceToHost, s->stream));
+            } else {
+                CU(cudaMemcpyAsync(W.data(), d_src, sizeof(double) * s->fieldlen, cudaMemcpyDeviceToHost, s->stream));
+            }
+
+            CU(cudaStreamSynchronize(s->stream));
+
+            if (d_tmp) {
+                cudaFreeAsync(d_tmp, s->stream);
+            }
+
+            return 0;
+        };
+        std::vector<double> W, Wim;
+        int drc = download(s->d_field, W);
+
+        if (drc == 0 && s->cfg.isrf) {
+            drc = download(s->d_field_im, Wim);
         }
 
-        CU(cudaStreamSynchronize(s->stream));
-
-        if (d_tmp) {
-            cudaFreeAsync(d_tmp, s->stream);
+        if (drc) {
+            return drc;
         }
 
         tr.mark("fetch: volume D2H");
@@ -1725,17 +1917,140 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
 
             for (int j = 0; j < c.srcnum; j++) {
                 double eabs = out->energytot[j] - out->energyesc[j];       // src/mmc_cu_host.cu:988
-                sum += normalize_field(s, W.data(), j == 0 && !dref.empty() ? dref.data() : NULL, (float)eabs, (float)out->energytot[j], j);
+                sum += normalize_field(s, W.data(), (s->cfg.isrf && c.srcnum == 1) ? Wim.data() : NULL, j == 0 && !dref.empty() ? dref.data() : NULL,
+                                       (float)eabs, (float)out->energytot[j], j);
             }
 
             out->normalizer = sum / c.srcnum;
+
+            // the slots behind the first get the average normaliser (and the nodal-volume division), src/mmc_cu_host.cu:997-1060
+            if (nslots > c.srcnum) {
+                const size_t datalen = (size_t)s->cfg.datalen, stride = datalen * s->cfg.maxgate;
+                const bool basis1 = (!s->isgrid && c.basisorder);
+
+                for (int slot = c.srcnum; slot < nslots; slot++) {
+                    for (size_t k = 0; k < stride; k++) {
+                        const size_t idx = (size_t)slot * stride + k;
+
+                        if (basis1 && m.nvol[k % datalen] > 0.f) {
+                            W[idx] /= m.nvol[k % datalen];
+
+                            if (!Wim.empty()) {
+                                Wim[idx] /= m.nvol[k % datalen];
+                            }
+                        }
+
+                        W[idx] *= out->normalizer;
+
+                        if (!Wim.empty()) {
+                            Wim[idx] *= (float)out->normalizer;
+                        }
+                    }
+                }
+            }
         }
 
         for (size_t i = 0; i < s->fieldlen; i++) {
             out->field[i] += W[i];          // cfg->exportfield[i] += field[i]  (src/mmc_cu_host.cu:918-920)
         }
 
+        if (out->field_im && !Wim.empty()) {
+            for (size_t i = 0; i < s->fieldlen; i++) {
+                out->field_im[i] += Wim[i];
+            }
+        }
+
         tr.mark("fetch: normalise+accumulate");
+
+        // ---- adjoint Jacobians from the slots' fluence (src/mmc_cu_host.cu:1063-1395): the normalised volumes go back to the
+        //      device as floats, one pass sums the gates per slot, the pair kernels write [datalen][Ns*Nd] per component
+        if (out->jacob && s->cfg.adj_ns > 0 && s->cfg.adj_nd > 0) {
+            const int Ns = s->cfg.adj_ns, Nd = s->cfg.adj_nd, dual = s->cfg.adj_dual, rf = s->cfg.isrf;
+            const size_t N = (size_t)s->cfg.datalen, adjlen = N * Ns * Nd, single = adjlen * (rf ? 2 : 1);
+            std::vector<float> hf(s->fieldlen);
+            float* d_f = NULL, *d_cwr = NULL, *d_cwi = NULL, *d_j1 = NULL, *d_j2 = NULL, *d_evol = NULL, *d_nvol = NULL;
+            CU(cudaMallocAsync(&d_f, sizeof(float) * s->fieldlen, s->stream));
+            CU(cudaMallocAsync(&d_cwr, sizeof(float) * N * nslots, s->stream));
+
+            for (int part = 0; part < (rf ? 2 : 1); part++) {
+                const std::vector<double>& src = part ? Wim : W;
+
+                for (size_t i = 0; i < s->fieldlen; i++) {
+                    hf[i] = (float)src[i];
+                }
+
+                if (part) {
+                    CU(cudaMallocAsync(&d_cwi, sizeof(float) * N * nslots, s->stream));
+                }
+
+                CU(cudaMemcpyAsync(d_f, hf.data(), sizeof(float) * s->fieldlen, cudaMemcpyHostToDevice, s->stream));
+                CUK(mmcb_k_adj_cw(d_f, part ? d_cwi : d_cwr, N, s->cfg.maxgate, nslots, s->stream));
+                CU(cudaStreamSynchronize(s->stream));       // hf is reused
+            }
+
+            const bool want_mua = (c.outputtype == MMCB_OT_ADJOINT || dual), want_d = (c.outputtype != MMCB_OT_ADJOINT);
+            CU(cudaMallocAsync(&d_j1, sizeof(float) * single, s->stream));
+            CU(cudaMemsetAsync(d_j1, 0, sizeof(float) * single, s->stream));
+
+            if (dual) {
+                CU(cudaMallocAsync(&d_j2, sizeof(float) * single, s->stream));
+                CU(cudaMemsetAsync(d_j2, 0, sizeof(float) * single, s->stream));
+            }
+
+            float* d_mua = want_mua ? d_j1 : NULL, *d_d = want_d ? (dual ? d_j2 : d_j1) : NULL;
+
+            if (s->isgrid) {        // :1253-1395, scaled by -Vvox (J_mua) and -unitinmm (J_D)
+                const float vvox = c.unitinmm * c.unitinmm * c.unitinmm;
+
+                if (d_mua) {
+                    CUK(mmcb_k_adj_mua(d_cwr, d_cwi, d_mua, N, Ns, Nd, -vvox, s->stream));
+                }
+
+                if (d_d) {
+                    CUK(mmcb_k_adj_dcoeff(d_cwr, d_cwi, d_d, N, Ns, Nd, (unsigned int)s->cfg.dim[0], (unsigned int)s->cfg.dim[1], -c.unitinmm, s->stream));
+                }
+            } else {                // :1067-1250
+                if ((rc_dev_alloc_float(&d_evol, m.evol, s->stream))) {
+                    return g_code;
+                }
+
+                if (d_mua && c.adjointmode == 1) {
+                    if ((rc_dev_alloc_float(&d_nvol, m.nvol, s->stream))) {
+                        return g_code;
+                    }
+
+                    CUK(mmcb_k_adj_mesh_nodal(d_cwr, d_cwi, d_nvol, d_mua, m.nn, Ns, Nd, s->stream));
+                }
+
+                if ((d_mua && c.adjointmode != 1) || d_d) {
+                    CUK(mmcb_k_adj_mesh_full(d_cwr, d_cwi, s->d_elem, s->d_node, d_evol, c.adjointmode == 1 ? NULL : d_mua, d_d, m.ne, m.nn, Ns, Nd,
+                                             s->stream));
+                }
+            }
+
+            // pack: CW [J1] | CW dual [J1, J2] | RF [Re J1, Im J1] | RF dual [Re J1, Re J2, Im J1, Im J2]
+            if (!dual) {
+                CU(cudaMemcpyAsync(out->jacob, d_j1, sizeof(float) * single, cudaMemcpyDeviceToHost, s->stream));
+            } else {
+                CU(cudaMemcpyAsync(out->jacob, d_j1, sizeof(float) * adjlen, cudaMemcpyDeviceToHost, s->stream));
+                CU(cudaMemcpyAsync(out->jacob + adjlen, d_j2, sizeof(float) * adjlen, cudaMemcpyDeviceToHost, s->stream));
+
+                if (rf) {
+                    CU(cudaMemcpyAsync(out->jacob + 2 * adjlen, d_j1 + adjlen, sizeof(float) * adjlen, cudaMemcpyDeviceToHost, s->stream));
+                    CU(cudaMemcpyAsync(out->jacob + 3 * adjlen, d_j2 + adjlen, sizeof(float) * adjlen, cudaMemcpyDeviceToHost, s->stream));
+                }
+            }
+
+            CU(cudaStreamSynchronize(s->stream));
+
+            for (float* q : {d_f, d_cwr, d_cwi, d_j1, d_j2, d_evol, d_nvol}) {
+                if (q) {
+                    cudaFreeAsync(q, s->stream);
+                }
+            }
+
+            tr.mark("fetch: adjoint Jacobian");
+        }
     }
 
     if (out->dref && !dref.empty()) {

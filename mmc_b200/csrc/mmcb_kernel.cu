@@ -100,6 +100,8 @@ struct Photon {
     unsigned int posidx;
     unsigned int id;
     int   fixcount;
+    unsigned int slotoff;      // multi-slot sources: offset of the photon's slot block in the volume
+    float w_im, oldw_im;       // RF variants: imaginary weight and pending imaginary deposit (src/mmc_core.cl:377,383)
 };
 
 // rotatevector, src/mmc_core.cl:1307-1330
@@ -210,6 +212,54 @@ __device__ __forceinline__ void launch_photon(Photon& p, Rng& rng, const mmcb_ka
     p.oldw = 0.f;
     p.posidx = 0;
     p.fixcount = 0;
+    p.slotoff = 0;
+    p.w_im = 0.f;
+    p.oldw_im = 0.f;
+
+    if (GENERAL && gp.multisrc) {       // multi-slot sources (adjoint mode), src/mmc_core.cl:1431-1515
+        unsigned int slot;
+
+        if (gp.srcid < 0) {             // every photon picks a slot; its deposits go to that slot's block of the volume
+            slot = min((unsigned int)(rand01(rng) * gp.extrasrclen), (unsigned int)gp.extrasrclen - 1u);
+            p.posidx = slot;
+            p.slotoff = slot * gp.slotstride;
+        } else {
+            slot = (unsigned int)(gp.srcid - 1);
+        }
+
+        const float4 sp = __ldg(a.srcdata + 4 * slot), sd = __ldg(a.srcdata + 4 * slot + 1);
+        const float radius = __ldg(&a.srcdata[4 * slot + 2].x);
+        const int slot_eid = (int)__ldg(&a.srcdata[4 * slot + 3].w);
+        p.px = sp.x;
+        p.py = sp.y;
+        p.pz = sp.z;
+        p.vx = sd.x;
+        p.vy = sd.y;
+        p.vz = sd.z;
+
+        if (radius > 0.f) {             // detector-as-source: uniform disk of the detector radius (:1470-1489)
+            float sphi, cphi;
+            sincosf(TWO_PI_F * rand01(rng), &sphi, &cphi);
+            const float r0 = sqrtf(rand01(rng)) * radius;
+
+            if (sd.z > -1.f + EPS && sd.z < 1.f - EPS) {
+                const float tmp0 = 1.f - sd.z * sd.z;
+                const float tmp1 = r0 * rsqrtf(tmp0);
+                p.px += tmp1 * (sd.x * sd.z * cphi - sd.y * sphi);
+                p.py += tmp1 * (sd.y * sd.z * cphi + sd.x * sphi);
+                p.pz -= tmp1 * tmp0 * cphi;
+            } else {
+                p.px += r0 * cphi;
+                p.py += r0 * sphi;
+            }
+        }
+
+        p.w = sp.w;                     // importance weight of the slot
+        p.eid = (slot_eid > 0) ? slot_eid : gp.e0;
+        p.slen = rand_scatlen(rng);
+        return;
+    }
+
     p.slen = rand_scatlen(rng);
     const int st = gp.srctype;
 
@@ -506,7 +556,7 @@ __device__ __forceinline__ float4 launch_bary(const Photon& p, const mmcb_kargs&
         return make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
-    if (gp.srctype == 0 || (p.eid == gp.e0 && (gp.srctype == 1 || gp.srctype == 2 || gp.srctype == 7))) {
+    if (!gp.multisrc && (gp.srctype == 0 || (p.eid == gp.e0 && (gp.srctype == 1 || gp.srctype == 2 || gp.srctype == 7)))) {
         return make_float4(gp.bary0[0], gp.bary0[1], gp.bary0[2], gp.bary0[3]);
     }
 
@@ -731,7 +781,7 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
         gate = min((int)((p.t - gp.tstart) * gp.Rtstep), gp.maxgate - 1);
     }
 
-    const unsigned int tshift = (unsigned int)gate * gp.framelen;
+    const unsigned int tshift = (unsigned int)gate * gp.framelen + (GENERAL ? p.slotoff : 0u);
 
     if (!nodal) {
         flush_deposit<GENERAL>(gfield, (unsigned int)(p.eid - 1) + tshift, ww, p, a, hot);
@@ -785,9 +835,10 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
 #ifndef MMCB_MINBLOCKS_HP
 #define MMCB_MINBLOCKS_HP 4
 #endif
-template <int METHOD, bool DET, bool GENERAL>
+template <int METHOD, bool DET, bool GENERAL, bool RF = false>
 __global__ void __launch_bounds__(MMCB_MAXTHREADS, (METHOD <= 1) ? MMCB_MINBLOCKS_HP : MMCB_MINBLOCKS)
 mmcb_photon_kernel(const mmcb_kargs a) {
+    static_assert(!RF || (GENERAL && METHOD >= 3), "RF forward runs use the general branch-less Badouel kernels");
     constexpr bool GRID = (METHOD == 4);
     constexpr bool HP = (METHOD <= 1);          // Havel / Plucker: 256-byte records, CPU-file semantics (src/mmc_raytrace.c)
     const bool hot = gp.hotcache != 0 && a.hotstat[MMCB_HOT_STAT_USEFUL] != 0;
@@ -800,6 +851,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
     const unsigned FULL = 0xFFFFFFFFu;
     acc_t* field = (acc_t*)a.field;
     const unsigned long long gfield = (unsigned long long)__cvta_generic_to_global(a.field);
+    const unsigned long long gfield_im = RF ? (unsigned long long)__cvta_generic_to_global(a.field_im) : 0ull;
 
     for (int i = threadIdx.x; i < 2 * gp.nmedia; i += blockDim.x) {      // {mua mus g n}, {1/mus n/c0 1/mua c0/n} per medium
         smed[i] = a.med[i];
@@ -1036,32 +1088,59 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 gate = min((int)(a.replaytime[p.id] * gp.Rtstep), gp.maxgate - 1);
             }
 
-            const unsigned int tshift = (unsigned int)gate * gp.framelen;
+            const unsigned int tshift = (unsigned int)gate * gp.framelen + (GENERAL ? p.slotoff : 0u);
 
             if (gp.outputtype != 2 && gp.outputtype != 4 && gp.outputtype != 5) {       // :844-851
                 ww = (pd.z == 0.f) ? (currweight * Lmove) : (ww * pd.z);
             }
 
             const bool flushnow = timeup || !isend;
+            // RF forward (omega > 0): the weight is complex, w *= exp(-(mua + i omega n/c0) L), and a step deposits
+            // (w0 - w1) / (mua + i omega n/c0)  (src/mmc_core.cl:872-896 mesh, :1043-1078 per dual-grid segment)
+            const float a_im = RF ? gp.omega * rc : 0.f;
+            const float a_mag2 = prop.x * prop.x + a_im * a_im;
+            float ww_im = 0.f;
 
             if (!GRID) {                                    // :856-1010: run-length merge of deposits into one accumulator
                 const unsigned int newidx = (unsigned int)(p.eid - 1) + tshift;
+
+                if constexpr (RF) {
+                    const float att = (totalloss < 1.f) ? (1.f - totalloss) : 1.f;      // exp(-mua L)
+                    float sph, cph;
+                    __sincosf(a_im * Lmove, &sph, &cph);
+                    const float w0r = currweight, w0i = p.w_im;
+                    const float nr = att * (w0r * cph + w0i * sph), ni = att * (-w0r * sph + w0i * cph);
+                    const float dr = w0r - nr, di = w0i - ni;
+                    ww = (a_mag2 > 0.f) ? __fdividef(dr * prop.x + di * a_im, a_mag2) : (w0r * Lmove);
+                    ww_im = (a_mag2 > 0.f) ? __fdividef(di * prop.x - dr * a_im, a_mag2) : (w0i * Lmove);
+                    p.w = nr;
+                    p.w_im = ni;
+                }
+
                 #pragma unroll
 
                 for (int k = 0; k < 2; k++) {               // k == 1 is the closing flush (one deposit site)
                     const unsigned int idx = (k == 0) ? newidx : (flushnow ? 0xFFFFFFFFu : newidx);
 
                     if (idx != p.oldidx) {
-                        if (p.oldw > 0.f) {
+                        // RF: the real part of a merged run may be <= 0; like the reference, a run that ends because the
+                        // element changed is dropped then (:907), the closing flush is unconditional (:961-984)
+                        if (RF ? (p.oldidx != 0xFFFFFFFFu && (k == 1 || p.oldw > 0.f)) : (p.oldw > 0.f)) {
                             flush_deposit<GENERAL>(gfield, p.oldidx, p.oldw, p, a, hot);
+
+                            if constexpr (RF) {
+                                red_global(gfield_im + (unsigned long long)p.oldidx * sizeof(acc_t), p.oldw_im, (acc_t*)0);
+                            }
                         }
 
                         p.oldidx = idx;
                         p.oldw = 0.f;
+                        p.oldw_im = 0.f;
                     }
 
                     if (k == 0) {
                         p.oldw += ww;
+                        p.oldw_im += ww_im;
                     }
                 }
             } else {                                        // dual-grid deposit :1022-1206
@@ -1072,6 +1151,11 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 float sx = (p.px - gp.nmin[0]) + dx * 0.5f, sy = (p.py - gp.nmin[1]) + dy * 0.5f, sz = (p.pz - gp.nmin[2]) + dz * 0.5f;
                 float frac = (totalloss == 0.f) ? 0.f : (1.f - segdecay) / totalloss;
                 float segw = ww;
+                float seg_re = currweight, seg_im = p.w_im, dsn = 0.f, dcs = 1.f;
+
+                if constexpr (RF) {
+                    __sincosf(a_im * seglen, &dsn, &dcs);
+                }
 
                 // consecutive segments in one voxel are merged before they reach the volume (the reference issues one atomic
                 // per segment once the photon is about to leave the element, src/mmc_core.cl:1150-1206): same sums, fewer
@@ -1089,21 +1173,41 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                     }
 
                     if (newidx != p.oldidx) {
-                        if (p.oldw > 0.f) {
+                        if (RF ? (p.oldidx != 0xFFFFFFFFu) : (p.oldw > 0.f)) {      // RF: ungated like :1084-1112
                             flush_deposit<GENERAL>(gfield, p.oldidx, p.oldw, p, a, hot);
+
+                            if constexpr (RF) {
+                                red_global(gfield_im + (unsigned long long)p.oldidx * sizeof(acc_t), p.oldw_im, (acc_t*)0);
+                            }
                         }
 
                         p.oldidx = newidx;
                         p.oldw = 0.f;
+                        p.oldw_im = 0.f;
                     }
 
                     if (k < seg) {
-                        p.oldw += segw * frac;
+                        if constexpr (RF) {
+                            const float w0r = seg_re, w0i = seg_im;
+                            seg_re = segdecay * (w0r * dcs + w0i * dsn);
+                            seg_im = segdecay * (-w0r * dsn + w0i * dcs);
+                            const float dr = w0r - seg_re, di = w0i - seg_im;
+                            p.oldw += (a_mag2 < EPS) ? (w0r * segw) : __fdividef(dr * prop.x + di * a_im, a_mag2);
+                            p.oldw_im += (a_mag2 < EPS) ? (w0i * segw) : __fdividef(di * prop.x - dr * a_im, a_mag2);
+                        } else {
+                            p.oldw += segw * frac;
+                        }
+
                         segw *= segdecay;
                         sx += dx;
                         sy += dy;
                         sz += dz;
                     }
+                }
+
+                if constexpr (RF) {                         // :1209-1212
+                    p.w = seg_re;
+                    p.w_im = seg_im;
                 }
             }
 
@@ -1164,9 +1268,14 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 // ---- end of the scattering path: roulette :2101-2114, then a new direction :2117-2135
                 bool dead = false;
 
-                if (p.w < gp.roulette_w) {                  // roulette_w = minenergy when roulette applies, else -1
+                if ((RF ? sqrtf(p.w * p.w + p.w_im * p.w_im) : p.w) < gp.roulette_w) {  // roulette_w = minenergy when roulette applies, else -1
                     if (rand01(rng) * gp.roulettesize <= 1.f) {
                         p.w *= gp.roulettesize;
+
+                        if constexpr (RF) {
+                            p.w_im *= gp.roulettesize;      // :2105-2107
+                        }
+
                     } else {
                         dead = true;
                     }
@@ -1234,7 +1343,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
             }
 
             if (!GENERAL || gp.srcnum == 1) {
-                eesc += p.w;
+                eesc += RF ? sqrtf(p.w * p.w + p.w_im * p.w_im) : p.w;     // RF: |w| (:2150-2152)
             } else {
                 for (int k = 0; k < gp.srcnum; k++) {
                     red_add_d(a.energy + MMCB_MAX_SRCNUM + k, (double)(p.w * a.srcpattern[(size_t)p.posidx * gp.srcnum + k]));
@@ -1274,7 +1383,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                             PPATH(reclen - 2) = p.vz;
                         }
 
-                        out[0] = (float)detid;
+                        out[0] = (float)((GENERAL && gp.multisrc && gp.srcid <= 0) ? ((unsigned int)detid | ((p.posidx + 1u) << 16)) : (unsigned int)detid);   // :652-658
 
                         for (int k = 0; k < reclen; k++) {
                             out[1 + k] = PPATH(k);
@@ -1543,7 +1652,15 @@ static photon_kernel_t pick_kernel(int isdet, int isgeneral) {
 
     return isgeneral ? mmcb_photon_kernel<METHOD, false, true> : mmcb_photon_kernel<METHOD, false, false>;
 }
-static photon_kernel_t pick_kernel(int method, int isdet, int isgeneral) {
+static photon_kernel_t pick_kernel(int method, int isdet, int isgeneral, int isrf) {
+    if (isrf) {         // RF forward: general branch-less Badouel kernels only (mesh or dual-grid deposit)
+        if (method == 4) {
+            return isdet ? mmcb_photon_kernel<4, true, true, true> : mmcb_photon_kernel<4, false, true, true>;
+        }
+
+        return isdet ? mmcb_photon_kernel<3, true, true, true> : mmcb_photon_kernel<3, false, true, true>;
+    }
+
     switch (method) {
         case 0:
             return pick_kernel<0>(isdet, isgeneral);
@@ -1559,8 +1676,8 @@ static photon_kernel_t pick_kernel(int method, int isdet, int isgeneral) {
     }
 }
 
-extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int method, int isdet, int isgeneral, cudaStream_t st) {
-    photon_kernel_t k = pick_kernel(method, isdet, isgeneral);
+extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int method, int isdet, int isgeneral, int isrf, cudaStream_t st) {
+    photon_kernel_t k = pick_kernel(method, isdet, isgeneral, isrf);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 
     if (e != cudaSuccess) {
@@ -1571,8 +1688,8 @@ extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, s
     return (int)cudaGetLastError();
 }
 
-extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int* blocks_per_sm) {
-    photon_kernel_t k = pick_kernel(method, isdet, isgeneral);
+extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int* blocks_per_sm) {
+    photon_kernel_t k = pick_kernel(method, isdet, isgeneral, isrf);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 
     if (e == cudaSuccess) {

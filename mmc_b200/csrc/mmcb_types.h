@@ -89,6 +89,12 @@ struct mmcb_kparam {
     int   hotcache;              // 1: kargs.hotkeys holds MMCB_HOT_SLOTS group keys, deposits to those groups go to shared memory
     unsigned int fieldlen;       // accumulator volume entries (guards the flush of the last, partial group)
     float hotshare;              // the cache is used when the hottest line holds more than this share of the deposited weight
+    // multi-slot sources (adjoint mode; src/mmc_core.cl:1431-1515) and RF (frequency-domain) forward runs (:872-896,1043-1078)
+    int   multisrc;              // 1: photons are launched from kargs.srcdata[] slots
+    int   srcid;                 // < 0: every photon picks a slot uniformly (field has one block per slot); > 0: only slot srcid-1
+    int   extrasrclen;           // slots in kargs.srcdata
+    unsigned int slotstride;     // framelen * maxgate: offset between the slots' blocks of the accumulator volume
+    float omega;                 // modulation angular frequency (rad/s); > 0 only in the RF kernel variants
 };
 
 struct mmcb_kargs {
@@ -107,6 +113,8 @@ struct mmcb_kargs {
     const float* replayweight;
     const float* replaytime;
     void*   field;               // accumulator volume
+    void*   field_im;            // RF: imaginary part, same layout
+    const float4* srcdata;       // multi-slot sources: 4 float4 per slot {srcpos(w: weight), srcdir(w: focal length), srcparam1, srcparam2(w: e0)}
     double* dref;
     float*  detected; unsigned int* detcount; unsigned long long* detseed;
     float*  traj;     unsigned int* trajcount;
