@@ -49,3 +49,31 @@ def test_bin_round_trip(tmp_path):
     f = str(tmp_path / "v.bin")
     mch.savebin(f, a)
     assert np.array_equal(mch.loadbin(f, 3), a)
+
+
+def test_nii_and_jnii_volume_round_trip(tmp_path):
+    """`-F nii` / `-F jnii` volumes (mcx_savenii src/mmc_utils.c:515-611, mcx_savejnii :787-905): header fields the reference
+    writes (dims x,y,z,t; voxel size; gate width in microseconds; float64 payload at offset 352) and a loss-less round trip."""
+    import json
+    import struct
+
+    from mmc_b200 import volio
+    rs = np.random.RandomState(2)
+    vol = rs.rand(3, 4, 5, 6)                                  # [gate, z, y, x]
+    p = str(tmp_path / "v.nii")
+    volio.savenii(p, vol, steps=(0.5, 0.5, 0.5), tstep=1e-10)
+    raw = open(p, "rb").read()
+    assert len(raw) == 352 + vol.size * 8
+    assert struct.unpack_from("<i", raw, 0)[0] == 348 and raw[344:348] == b"n+1\0"
+    assert struct.unpack_from("<8h", raw, 40) == (4, 6, 5, 4, 3, 0, 0, 0)
+    assert struct.unpack_from("<2h", raw, 70) == (64, 64)       # NIFTI_TYPE_FLOAT64, bitpix
+    assert struct.unpack_from("<f", raw, 108)[0] == 352.0
+    assert abs(struct.unpack_from("<8f", raw, 76)[4] - 1e-4) < 1e-9   # tstep in microseconds
+    r = volio.loadnii(p)
+    assert np.array_equal(r["vol"], vol) and r["steps"] == (0.5, 0.5, 0.5)
+    p = str(tmp_path / "v.jnii")
+    volio.savejnii(p, vol.astype(np.float32), steps=(0.5, 0.5, 0.5), tstep=1e-10)
+    j = json.load(open(p))
+    assert j["NIFTIHeader"]["Dim"] == [6, 5, 4, 3] and j["NIFTIHeader"]["DataType"] == "single"
+    assert j["NIFTIData"]["_ArrayZipType_"] == "zlib" and j["NIFTIData"]["_ArraySize_"] == [6, 5, 4, 3]
+    assert np.array_equal(volio.loadjnii(p)["vol"], vol.astype(np.float32))
