@@ -289,9 +289,11 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ne, nn = len(cfg["elem"]), len(cfg["node"])
         nthread = 148 * 8 * 128
-        h2d = ne * 96 + ne * 16 + ne * 16 + nn * 12 + 16 * nthread        # records, centroids, elem, nodes, seed words
+        # elem (twice: face-neighbour pass + session table), numbered face neighbours, labels, nodes, seed words; the 96-byte records and
+        # the centroids are built on the device.  D2H: the volume + the raw face-neighbour table (numbered on the host)
+        h2d = ne * 16 * 2 + ne * 16 + ne * 4 + nn * 12 + 16 * nthread
         e2e = {"value": world * nphoton * reps / float(tt[0]), "unit": "photons/ms", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(r["raw"].size * 8), "ms": float(tt[0]) / reps, "kernel_ms": float(np.mean(e2e_kern)), "runs": reps}
+               "d2h_bytes_per_step": int(r["raw"].size * 8 + ne * 16), "ms": float(tt[0]) / reps, "kernel_ms": float(np.mean(e2e_kern)), "runs": reps}
 
     if rank != 0:
         if dist is not None:

@@ -205,6 +205,9 @@ int  mmcb_get_sizes(mmcb_session* s, mmcb_sizes* sizes);
  * session's own tallies, or point to globally reduced values (multi-GPU). */
 int  mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc, mmcb_output* out);
 int  mmcb_reset(mmcb_session* s);            /* zero all accumulators */
+/* diagnostics: the session's device tables -- ne 96-byte tetrahedron records (tracer_build planes + neighbours + flags), ne*4 centroid
+ * floats -- and the prepared face-neighbour table (ne*4, exterior faces numbered -1..-nf like tracer_prep); any pointer may be NULL */
+int  mmcb_get_tables(mmcb_session* s, void* tetrec_out, float* cent_out, int* facenb_out);
 void mmcb_destroy(mmcb_session* s);
 
 /* ---- host-side mesh helpers (what mmc_prep/tracer_prep compute; exposed for callers and tests) ------- */

@@ -100,7 +100,7 @@ class DevPtrs(C.Structure):
 
 EXPORTS = ["mmcb_version", "mmcb_last_error", "mmcb_list_gpu", "mmcb_query_sizes", "mmcb_run_simulation",
            "mmcb_create", "mmcb_set_field_buffer", "mmcb_launch", "mmcb_sync", "mmcb_last_kernel_ms",
-           "mmcb_get_devptrs", "mmcb_get_sizes", "mmcb_fetch", "mmcb_reset", "mmcb_destroy",
+           "mmcb_get_devptrs", "mmcb_get_sizes", "mmcb_fetch", "mmcb_reset", "mmcb_destroy", "mmcb_get_tables",
            "mmcb_mesh_volumes", "mmcb_mesh_facenb", "mmcb_mesh_initelem", "mmcb_host_seeds", "mmcb_rng_selftest"]
 
 _lib = None
@@ -129,6 +129,7 @@ def lib():
         L.mmcb_get_sizes.argtypes = [C.c_void_p, C.POINTER(Sizes)]
         L.mmcb_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Output)]
         L.mmcb_reset.argtypes = [C.c_void_p]
+        L.mmcb_get_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mmcb_list_gpu.argtypes = [C.POINTER(GpuInfo), C.c_int]
         L.mmcb_mesh_volumes.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mmcb_mesh_facenb.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
@@ -457,6 +458,15 @@ class Session:
         d = DevPtrs()
         _check(lib().mmcb_get_devptrs(self.h, C.byref(d)))
         return d
+
+    def tables(self):
+        """Diagnostics: (records uint32 [ne, 24], centroids float32 [ne, 4], facenb int32 [ne, 4]) as the session holds them."""
+        ne = len(self.prob.elem)
+        rec = np.zeros((ne, 24), dtype=np.uint32)
+        cent = np.zeros((ne, 4), dtype=np.float32)
+        fnb = np.zeros((ne, 4), dtype=np.int32)
+        _check(lib().mmcb_get_tables(self.h, rec.ctypes.data, cent.ctypes.data, fnb.ctypes.data))
+        return rec, cent, fnb
 
     def set_field_buffer(self, device_ptr):
         _check(lib().mmcb_set_field_buffer(self.h, C.c_void_p(device_ptr)))

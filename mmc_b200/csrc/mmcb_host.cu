@@ -23,6 +23,10 @@
 extern "C" int mmcb_k_upload_param(const mmcb_kparam* hp, const float* det4, int detnum, cudaStream_t st);
 extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int method, int isdet, int isgeneral, int isrf, cudaStream_t st);
 extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int* blocks_per_sm);
+// mesh pre-processing on the device (mmcb_prep.cu)
+extern "C" int mmcb_k_facenb(const int* d_elem, int ne, int* d_facenb, cudaStream_t st);
+extern "C" int mmcb_k_build_records(const float* d_node, const int* d_elem, const int* d_facenb, const int* d_type, const float* d_med_n, int ne,
+                                    float nout, int isreflect, mmcb_tetrec* d_rec, float4* d_cent, cudaStream_t st);
 // adjoint-Jacobian post-kernels (mmcb_adjoint.cu)
 extern "C" int mmcb_k_adj_cw(const float* field, float* cw, size_t N, int maxgate, int nslots, cudaStream_t st);
 extern "C" int mmcb_k_adj_mua(const float* cw_re, const float* cw_im, float* out, size_t N, int Ns, int Nd, float scale, cudaStream_t st);
@@ -520,7 +524,9 @@ int validate(const mmcb_config* in, const mmcb_mesh* mesh, Cfg& o) {
     return 0;
 }
 
-int prepare_mesh(const mmcb_mesh* in, Cfg& cfg, PrepMesh& m) {
+// gpu_stream: when not NULL (session path, device selected) the face-neighbour table is built on the device (mmcb_prep.cu);
+// the host sort remains for mmcb_query_sizes / mmcb_mesh_facenb, which must work without a GPU
+int prepare_mesh(const mmcb_mesh* in, Cfg& cfg, PrepMesh& m, cudaStream_t gpu_stream = NULL, bool use_gpu = false) {
     mmcb_config& c = cfg.c;
 
     if (in->nn <= 0 || in->ne <= 0 || !in->node || !in->elem || !in->type || !in->med || in->prop < 1) {
@@ -613,6 +619,16 @@ int prepare_mesh(const mmcb_mesh* in, Cfg& cfg, PrepMesh& m) {
         for (size_t i = 0; i < m.facenb.size(); i++) {
             m.facenb[i] = in->facenb[i] > 0 ? in->facenb[i] : 0;
         }
+    } else if (use_gpu && m.nn < (1 << 21) && !getenv("MMCB_HOST_PREP")) {
+        int* d_e = NULL, *d_f = NULL;
+        CU(cudaMallocAsync(&d_e, sizeof(int) * m.elem.size(), gpu_stream));
+        CU(cudaMallocAsync(&d_f, sizeof(int) * m.elem.size(), gpu_stream));
+        CU(cudaMemcpyAsync(d_e, m.elem.data(), sizeof(int) * m.elem.size(), cudaMemcpyHostToDevice, gpu_stream));
+        CUK(mmcb_k_facenb(d_e, m.ne, d_f, gpu_stream));
+        CU(cudaMemcpyAsync(m.facenb.data(), d_f, sizeof(int) * m.elem.size(), cudaMemcpyDeviceToHost, gpu_stream));
+        CU(cudaStreamSynchronize(gpu_stream));
+        cudaFreeAsync(d_e, gpu_stream);
+        cudaFreeAsync(d_f, gpu_stream);
     } else {
         facenb_build(m.ne, m.elem.data(), m.facenb.data());
     }
@@ -1035,13 +1051,6 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
         return rc;
     }
 
-    rc = prepare_mesh(meshin, s->cfg, s->mesh);
-
-    if (rc) {
-        return rc;
-    }
-
-    tr.mark("validate+prepare_mesh");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
 
@@ -1065,6 +1074,13 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
     tr.mark("device+stream");
+    rc = prepare_mesh(meshin, s->cfg, s->mesh, s->stream, true);
+
+    if (rc) {
+        return rc;
+    }
+
+    tr.mark("validate+prepare_mesh");
     const mmcb_config& c = s->cfg.c;
     const PrepMesh& m = s->mesh;
     s->acc_double = mmcb_k_acc_is_double() != 0;
@@ -1091,35 +1107,60 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     }
 
     // tables
-    std::vector<mmcb_tetrec> rec;
-    std::vector<float> cent;
-    build_records(m, s->cfg, rec, cent);
-    tr.mark("build_records");
-    rc = dev_alloc_copy(&s->d_tet, rec.data(), rec.size());
-
-    if (rc) {
-        return rc;
-    }
-
-    if (s->ishp) {
-        std::vector<mmcb_tetrec_big> big;
-        build_records_big(m, s->cfg, rec, big);
-
-        if ((rc = dev_alloc_copy(&s->d_tetbig, big.data(), big.size()))) {
-            return rc;
-        }
-    }
-
-    if ((rc = dev_alloc_copy((float**)&s->d_cent, cent.data(), cent.size()))) {
-        return rc;
-    }
-
     if ((rc = dev_alloc_copy(&s->d_node, m.node.data(), m.node.size()))) {
         return rc;
     }
 
     if ((rc = dev_alloc_copy(&s->d_elem, m.elem.data(), m.elem.size()))) {
         return rc;
+    }
+
+    if (!s->ishp && !getenv("MMCB_HOST_PREP")) {
+        // branch-less Badouel records and centroids are built on the device (mmcb_prep.cu): 20 bytes per element go up
+        // (neighbours + label) instead of 112 (records + centroids)
+        int* d_fnb = NULL, *d_type = NULL;
+        float* d_medn = NULL;
+        std::vector<float> medn(m.med.size());
+
+        for (size_t i = 0; i < m.med.size(); i++) {
+            medn[i] = m.med[i].n;
+        }
+
+        if ((rc = dev_alloc_copy(&d_fnb, m.facenb.data(), m.facenb.size())) || (rc = dev_alloc_copy(&d_type, m.type.data(), m.type.size())) ||
+                (rc = dev_alloc_copy(&d_medn, medn.data(), medn.size()))) {
+            return rc;
+        }
+
+        CU(cudaMallocAsync(&s->d_tet, sizeof(mmcb_tetrec) * (size_t)m.ne, s->stream));
+        CU(cudaMallocAsync(&s->d_cent, sizeof(float4) * (size_t)m.ne, s->stream));
+        CUK(mmcb_k_build_records(s->d_node, s->d_elem, d_fnb, d_type, d_medn, m.ne, c.nout, c.isreflect, s->d_tet, s->d_cent, s->stream));
+        dev_free(d_fnb);
+        dev_free(d_type);
+        dev_free(d_medn);
+        tr.mark("build_records (device)");
+    } else {
+        std::vector<mmcb_tetrec> rec;
+        std::vector<float> cent;
+        build_records(m, s->cfg, rec, cent);
+        tr.mark("build_records");
+        rc = dev_alloc_copy(&s->d_tet, rec.data(), rec.size());
+
+        if (rc) {
+            return rc;
+        }
+
+        if (s->ishp) {
+            std::vector<mmcb_tetrec_big> big;
+            build_records_big(m, s->cfg, rec, big);
+
+            if ((rc = dev_alloc_copy(&s->d_tetbig, big.data(), big.size()))) {
+                return rc;
+            }
+        }
+
+        if ((rc = dev_alloc_copy((float**)&s->d_cent, cent.data(), cent.size()))) {
+            return rc;
+        }
     }
 
     if ((rc = dev_alloc_copy(&s->d_srcelem, m.srcelem.data(), m.srcelem.size()))) {
@@ -1655,6 +1696,29 @@ int mmcb_get_devptrs(mmcb_session* s, mmcb_devptrs* p) {
     p->detseed = (uint64_t*)s->d_detseed;
     p->dref = s->d_dref;
     p->dreflen = (size_t)s->mesh.nf * s->cfg.maxgate;
+    return 0;
+}
+
+int mmcb_get_tables(mmcb_session* s, void* tetrec_out, float* cent_out, int* facenb_out) {
+    if (!s) {
+        return fail(MMCB_ERR_INPUT, "null session");
+    }
+
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+
+    if (tetrec_out) {
+        CU(cudaMemcpy(tetrec_out, s->d_tet, sizeof(mmcb_tetrec) * (size_t)s->mesh.ne, cudaMemcpyDeviceToHost));
+    }
+
+    if (cent_out) {
+        CU(cudaMemcpy(cent_out, s->d_cent, sizeof(float4) * (size_t)s->mesh.ne, cudaMemcpyDeviceToHost));
+    }
+
+    if (facenb_out) {
+        memcpy(facenb_out, s->mesh.facenb.data(), sizeof(int) * s->mesh.facenb.size());
+    }
+
     return 0;
 }
 
