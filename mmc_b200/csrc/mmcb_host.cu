@@ -938,6 +938,7 @@ struct mmcb_session {
     Cfg cfg;
     PrepMesh mesh;
     mmcb_kparam kp, kp_pilot;
+    size_t smem_scout = 0;         // shared memory of the scout launch (no detector columns, no cache)
     mmcb_kargs ka;
     cudaStream_t stream = NULL;
     cudaEvent_t ev0 = NULL, ev1 = NULL;
@@ -1279,6 +1280,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     s->block = std::max(32, (s->block / 32) * 32);
     s->smem_base = 2 * sizeof(float4) * m.med.size() + (s->isdet ? sizeof(float) * (size_t)devreclen * s->block : 0);
     s->hot_allowed = (c.hotcache >= 0 && srcnum == 1);
+    s->smem_scout = 2 * sizeof(float4) * m.med.size();
     // the grid (= number of RNG streams) is sized for the larger footprint so that pilot and main launch share it
     s->smem = s->smem_base + (s->hot_allowed ? sizeof(unsigned int) * MMCB_HOT_SLOTS + sizeof(float) * MMCB_HOT_SLOTS * MMCB_HOT_GROUP : 0);
 
@@ -1622,11 +1624,52 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
 
     CU(cudaMemcpyAsync(s->d_seeds, s->hseeds.data(), s->hseeds.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     const mmcb_config& c = s->cfg.c;
-    // first big launch of a session: a pilot batch (part of the requested photons) shows where the deposits pile up
-    const bool pilot = s->hot_allowed && !s->hot_ready && (c.hotcache > 0 ? nphoton >= 4096 : nphoton >= 500000);
+    // first big launch of a session: a pilot batch shows where the deposits pile up.  Time-resolved single-slot runs use a SCOUT: extra
+    // photons that live for the first time gate only and deposit into a scratch copy of that gate's block; they are discarded, so
+    // the scout costs ~0.1 % of the run and has no long-lived stragglers (the hottest lines are the early-time lines next to the
+    // source).  Other runs (one gate, multi-slot) take the pilot out of the requested photons and keep its results.
+    bool pilot = s->hot_allowed && !s->hot_ready && (c.hotcache > 0 ? nphoton >= 4096 : nphoton >= 500000);
     uint64_t n0 = pilot ? std::min<uint64_t>(std::max<uint64_t>(nphoton / 64, 16384), 262144) : 0;
     n0 = std::min(n0, nphoton / 2);
     CU(cudaEventRecord(s->ev0, st));
+
+    if (pilot && s->cfg.maxgate > 1 && s->cfg.nslots == 1 && !getenv("MMCB_NO_SCOUT")) {
+        const size_t flen = (size_t)s->kp.framelen * c.srcnum, accsize = s->acc_double ? 8 : 4;
+        char* scr = NULL;           // [volume of gate 0][energy tot/esc][raytet][detcount, trajcount]
+        const size_t tail = sizeof(double) * (2 * MMCB_MAX_SRCNUM + 1) + 2 * sizeof(unsigned int), voff = (flen * accsize + 15) / 16 * 16;
+        CU(cudaMallocAsync(&scr, voff + tail, st));
+        CU(cudaMemsetAsync(scr, 0, voff + tail, st));
+        mmcb_kparam& kp = s->kp_pilot;
+        kp = s->kp;
+        kp.maxgate = 1;
+        kp.tend = c.tstart + c.tstep;
+        kp.nphoton = n0;
+        kp.photon_offset = photon_offset;
+        kp.threadphoton = (int)(n0 / (uint64_t)s->nthread);
+        kp.oddphotons = (int)(n0 - (uint64_t)kp.threadphoton * s->nthread);
+        kp.hotcache = 0;
+        kp.savetraj = 0;
+        kp.issaveref = 0;
+        kp.issavedet = 0;
+        kp.fieldlen = (unsigned int)flen;
+        kp.omega = 0.f;
+        mmcb_kargs ka = s->ka;
+        ka.field = scr;
+        ka.field_im = NULL;
+        ka.dref = NULL;
+        ka.energy = (double*)(scr + voff);
+        ka.raytet = ka.energy + 2 * MMCB_MAX_SRCNUM;
+        ka.detcount = (unsigned int*)(ka.raytet + 1);
+        ka.trajcount = ka.detcount + 1;
+        CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
+        CUK(mmcb_k_upload_param(&kp, s->cfg.detpos.data(), c.detnum, st));
+        CUK(mmcb_k_launch_photons(&ka, s->grid, s->block, s->smem_scout, c.method, 0, s->isgeneral, 0, st));
+        CUK(mmcb_k_hot_select(scr, flen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys, c.hotcache > 0 ? 0.f : MMCB_HOT_MINSHARE, st));
+        CU(cudaFreeAsync(scr, st));
+        s->hot_ready = true;
+        pilot = false;
+        n0 = 0;
+    }
 
     for (int part = pilot ? 0 : 1; part < 2; part++) {
         const uint64_t n = (part == 0) ? n0 : nphoton - n0, off = (part == 0) ? photon_offset : photon_offset + n0;
