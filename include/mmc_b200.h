@@ -155,6 +155,9 @@ typedef struct mmcb_output {
     double* field_im;            /* RF forward: imaginary part of the fluence, same layout as `field` (cfg->exportadjoint); may be NULL */
     float*  jacob;               /* adjoint output types: sizes.jacoblen floats (cfg->exportjacob), layout [datalen][Ns*Nd] per component:
                                     CW [J1] | CW dual [J1, J2] | RF [Re J1, Im J1] | RF dual [Re J1, Re J2, Im J1, Im J2]; may be NULL */
+    int     overwrite;           /* 0: results are ADDED to field/dref/field_im like the reference adds to cfg->exportfield (default);
+                                    1: the arrays are stored (=) without being read: the normalised volume is copied from the device
+                                    straight into `field`, which saves a host pass for callers that hand in fresh buffers */
 } mmcb_output;
 
 typedef struct mmcb_sizes {

@@ -82,7 +82,7 @@ class Output(C.Structure):
                 ("detectedcount", C.c_uint), ("detectedtotal", C.c_uint), ("trajcount", C.c_uint),
                 ("energytot", C.c_double * 16), ("energyesc", C.c_double * 16),
                 ("raytet", C.c_double), ("normalizer", C.c_double), ("kernel_ms", C.c_float), ("e0", C.c_int),
-                ("field_im", C.c_void_p), ("jacob", C.c_void_p)]
+                ("field_im", C.c_void_p), ("jacob", C.c_void_p), ("overwrite", C.c_int)]
 
 
 class Sizes(C.Structure):
@@ -324,7 +324,7 @@ class Problem:
 class _OutBuffers:
     def __init__(self, prob, sz):
         c = prob.cfg
-        self.field = np.zeros(sz.fieldlen, dtype=np.float64)
+        self.field = np.empty(sz.fieldlen, dtype=np.float64)      # overwrite=1: filled by the library
         self.dref = np.zeros(max(1, sz.nf * sz.maxgate), dtype=np.float64) if c.issaveref else None
         nd = int(c.maxdetphoton) if c.issavedet else 0
         self.detected = np.zeros((max(nd, 1), sz.reclen), dtype=np.float32)
@@ -338,6 +338,7 @@ class _OutBuffers:
         o.detected, o.detseed, o.traj = self.detected.ctypes.data, self.detseed.ctypes.data, self.traj.ctypes.data
         o.field_im = self.field_im.ctypes.data if self.field_im is not None else None
         o.jacob = self.jacob.ctypes.data if self.jacob is not None else None
+        o.overwrite = 1          # fresh buffers: the library stores instead of accumulating (no host pass over the volume)
         self.out = o
         self.sz = sz
 

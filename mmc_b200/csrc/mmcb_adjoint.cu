@@ -302,3 +302,134 @@ extern "C" int mmcb_k_adj_mesh_nodal(const float* cw_re, const float* cw_im, con
     mmcb_adj_mesh_nodal_kernel<<<grid_for((size_t)nn), 256, 0, st>>>(cw_re, cw_im, nvol, jmua, nn, Ns, Nd);
     return (int)cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// mesh_normalize (src/mmc_mesh.c:2154-2279) on the device: the volume is reduced and scaled where it lives, and crosses PCIe once
+// in its final form (the reference downloads raw floats, then makes several host passes over the double volume).
+// Layout: W[(gate*datalen + i)*srcnum + pair], like mesh->weight.
+// ---------------------------------------------------------------------------------------------------------------------
+struct mmcb_normfac {
+    double f[16];
+};
+
+__device__ __forceinline__ void block_add(double v, double* dst) {
+    #pragma unroll
+
+    for (int o = 16; o > 0; o >>= 1) {
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    }
+
+    __shared__ double part[32];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+
+    if (l == 0) {
+        part[w] = v;
+    }
+
+    __syncthreads();
+
+    if (w == 0) {
+        v = (l < (blockDim.x >> 5)) ? part[l] : 0.0;
+        #pragma unroll
+
+        for (int o = 16; o > 0; o >>= 1) {
+            v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        }
+
+        if (l == 0) {
+            atomicAdd(dst, v);
+        }
+    }
+}
+
+// basisorder 0: energydeposit[pair] = sum of all entries of the pair (:2247-2250)
+__global__ void mmcb_norm_sum_kernel(const double* __restrict__ W, size_t nentry, int srcnum, double* __restrict__ dep) {
+    const int p = blockIdx.y;
+    double s = 0.0;
+
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < nentry; e += (size_t)gridDim.x * blockDim.x) {
+        s += W[e * srcnum + p];
+    }
+
+    block_add(s, dep + p);
+}
+
+// basisorder 1, step 1: W /= nvol[node] where nvol > 0 (:2213-2222)
+__global__ void mmcb_norm_nvol_kernel(double* __restrict__ W, size_t n, int nn, int srcnum, const float* __restrict__ nvol) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = nvol[(i / srcnum) % nn];
+
+        if (v > 0.f) {
+            W[i] /= v;
+        }
+    }
+}
+
+// basisorder 1, step 2: energydeposit[pair] = sum_e (sum_gates sum_4nodes (float)W) * evol_e * mua_e (:2224-2245)
+__global__ void mmcb_norm_elemdep_kernel(const double* __restrict__ W, const int* __restrict__ elem, const float* __restrict__ evol,
+        const float* __restrict__ emua, int ne, int nn, int maxgate, int srcnum, double* __restrict__ dep) {
+    const int p = blockIdx.y;
+    double s = 0.0;
+
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
+        const int4 ee = *(const int4*)(elem + 4 * (size_t)e);
+        double energyelem = 0.0;
+
+        for (int g = 0; g < maxgate; g++) {
+            const size_t base = (size_t)g * nn;
+            energyelem += (float)W[(base + ee.x - 1) * srcnum + p];
+            energyelem += (float)W[(base + ee.y - 1) * srcnum + p];
+            energyelem += (float)W[(base + ee.z - 1) * srcnum + p];
+            energyelem += (float)W[(base + ee.w - 1) * srcnum + p];
+        }
+
+        s += energyelem * evol[e] * emua[e];
+    }
+
+    block_add(s, dep + p);
+}
+
+// final pass: out = (in / (evol*mua)) * fac[pair]   (division only for basisorder 0, :2252-2258), out may alias in
+__global__ void mmcb_norm_scale_kernel(const double* __restrict__ in, double* __restrict__ out, size_t n, int datalen, int srcnum,
+                                       const float* __restrict__ evol, const float* __restrict__ emua, const mmcb_normfac fac) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double v = in[i];
+
+        if (evol) {
+            const size_t e = (i / srcnum) % datalen;
+            v /= (double)__fmul_rn(evol[e], emua[e]);
+        }
+
+        out[i] = v * fac.f[i % srcnum];
+    }
+}
+
+extern "C" int mmcb_k_norm_sum(const double* W, size_t nentry, int srcnum, double* dep, cudaStream_t st) {
+    dim3 g(grid_for(nentry), srcnum);
+    mmcb_norm_sum_kernel<<<g, 256, 0, st>>>(W, nentry, srcnum, dep);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int mmcb_k_norm_nvol(double* W, size_t n, int nn, int srcnum, const float* nvol, cudaStream_t st) {
+    mmcb_norm_nvol_kernel<<<grid_for(n), 256, 0, st>>>(W, n, nn, srcnum, nvol);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int mmcb_k_norm_elemdep(const double* W, const int* elem, const float* evol, const float* emua, int ne, int nn, int maxgate, int srcnum,
+                                   double* dep, cudaStream_t st) {
+    dim3 g(grid_for((size_t)ne), srcnum);
+    mmcb_norm_elemdep_kernel<<<g, 256, 0, st>>>(W, elem, evol, emua, ne, nn, maxgate, srcnum, dep);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int mmcb_k_norm_scale(const double* in, double* out, size_t n, int datalen, int srcnum, const float* evol, const float* emua,
+                                 const double* fac16, cudaStream_t st) {
+    mmcb_normfac f;
+
+    for (int i = 0; i < 16; i++) {
+        f.f[i] = fac16[i];
+    }
+
+    mmcb_norm_scale_kernel<<<grid_for(n), 256, 0, st>>>(in, out, n, datalen, srcnum, evol, emua, f);
+    return (int)cudaGetLastError();
+}

@@ -27,6 +27,13 @@ extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, i
 extern "C" int mmcb_k_facenb(const int* d_elem, int ne, int* d_facenb, cudaStream_t st);
 extern "C" int mmcb_k_build_records(const float* d_node, const int* d_elem, const int* d_facenb, const int* d_type, const float* d_med_n, int ne,
                                     float nout, int isreflect, mmcb_tetrec* d_rec, float4* d_cent, cudaStream_t st);
+// mesh_normalize on the device (mmcb_adjoint.cu)
+extern "C" int mmcb_k_norm_sum(const double* W, size_t nentry, int srcnum, double* dep, cudaStream_t st);
+extern "C" int mmcb_k_norm_nvol(double* W, size_t n, int nn, int srcnum, const float* nvol, cudaStream_t st);
+extern "C" int mmcb_k_norm_elemdep(const double* W, const int* elem, const float* evol, const float* emua, int ne, int nn, int maxgate, int srcnum,
+                                   double* dep, cudaStream_t st);
+extern "C" int mmcb_k_norm_scale(const double* in, double* out, size_t n, int datalen, int srcnum, const float* evol, const float* emua,
+                                 const double* fac16, cudaStream_t st);
 // adjoint-Jacobian post-kernels (mmcb_adjoint.cu)
 extern "C" int mmcb_k_adj_cw(const float* field, float* cw, size_t N, int maxgate, int nslots, cudaStream_t st);
 extern "C" int mmcb_k_adj_mua(const float* cw_re, const float* cw_im, float* out, size_t N, int Ns, int Nd, float scale, cudaStream_t st);
@@ -1977,7 +1984,144 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
                 st[MMCB_HOT_STAT_USEFUL], st[1], tot > 0.f ? mx / tot : 0.f);
     }
 
-    if (out->field) {
+    // ---- common case (one slot, no RF): mesh_normalize runs on the device and the volume crosses PCIe once, in its final form
+    if (out->field && !s->cfg.isrf && s->cfg.nslots == 1 && !getenv("MMCB_HOST_NORM")) {
+        const bool nodal = (!s->isgrid && !s->ishp && c.basisorder);
+        const size_t n = s->fieldlen;
+        const int datalen = s->cfg.datalen, maxgate = s->cfg.maxgate, srcnum = c.srcnum;
+        double* d_out = NULL;
+        const double* d_src = (const double*)s->d_field;
+
+        if (nodal) {
+            CU(cudaMallocAsync(&d_out, sizeof(double) * n, s->stream));
+            CU(cudaMemsetAsync(d_out, 0, sizeof(double) * n, s->stream));
+            CUK(mmcb_k_spread_nodes(s->d_field, d_out, s->d_elem, m.ne, m.nn, maxgate, srcnum, s->stream));
+            d_src = d_out;
+        } else if (!s->acc_double) {
+            CU(cudaMallocAsync(&d_out, sizeof(double) * n, s->stream));
+            CUK(mmcb_k_acc_to_double(s->d_field, d_out, n, s->stream));
+            d_src = d_out;
+        }
+
+        if (c.isnormalized) {
+            if (!d_out) {       // the accumulators stay untouched: the session may keep adding to them
+                CU(cudaMallocAsync(&d_out, sizeof(double) * n, s->stream));
+            }
+
+            const bool replay = (c.seed == MMCB_SEED_FROM_FILE && (c.outputtype == MMCB_OT_JACOBIAN || c.outputtype == MMCB_OT_WL || c.outputtype == MMCB_OT_WP));
+            const bool basis1 = (!s->isgrid && c.basisorder), basis0 = (!s->isgrid && !c.basisorder);
+            const bool needdep = !replay && c.outputtype != MMCB_OT_ENERGY && !s->isgrid;
+            double fac[16], dep[MMCB_MAX_SRCNUM];
+            double* d_dep = NULL;
+            float* d_evol = NULL, *d_emua = NULL, *d_nvol = NULL;
+
+            if (needdep) {
+                std::vector<float> emua(m.ne);
+
+                for (int i = 0; i < m.ne; i++) {
+                    emua[i] = m.med[m.type[i]].mua;
+                }
+
+                if (rc_dev_alloc_float(&d_evol, m.evol, s->stream) || rc_dev_alloc_float(&d_emua, emua, s->stream)) {
+                    return g_code;
+                }
+
+                CU(cudaMallocAsync(&d_dep, sizeof(double) * MMCB_MAX_SRCNUM, s->stream));
+                CU(cudaMemsetAsync(d_dep, 0, sizeof(double) * MMCB_MAX_SRCNUM, s->stream));
+
+                if (basis1) {
+                    if (rc_dev_alloc_float(&d_nvol, m.nvol, s->stream)) {
+                        return g_code;
+                    }
+
+                    if (d_src != d_out) {
+                        CU(cudaMemcpyAsync(d_out, d_src, sizeof(double) * n, cudaMemcpyDeviceToDevice, s->stream));
+                        d_src = d_out;
+                    }
+
+                    CUK(mmcb_k_norm_nvol(d_out, n, m.nn, srcnum, d_nvol, s->stream));
+                    CUK(mmcb_k_norm_elemdep(d_out, s->d_elem, d_evol, d_emua, m.ne, m.nn, maxgate, srcnum, d_dep, s->stream));
+                } else {
+                    CUK(mmcb_k_norm_sum(d_src, n / srcnum, srcnum, d_dep, s->stream));
+                }
+
+                CU(cudaMemcpyAsync(dep, d_dep, sizeof(double) * MMCB_MAX_SRCNUM, cudaMemcpyDeviceToHost, s->stream));
+                CU(cudaStreamSynchronize(s->stream));
+            }
+
+            double sum = 0;
+
+            for (int j = 0; j < 16; j++) {
+                fac[j] = 1.0;
+            }
+
+            for (int j = 0; j < srcnum; j++) {
+                const float Eabsorb = (float)(out->energytot[j] - out->energyesc[j]), Etotal = (float)out->energytot[j];   // :988, float args
+                double nz;
+
+                if (replay) {
+                    nz = (c.outputtype == MMCB_OT_JACOBIAN) ? 1.f / (1e-4f * c.nphoton) : 1.f / Etotal;
+                } else if (c.outputtype == MMCB_OT_ENERGY) {
+                    nz = 1.f / Etotal;
+                } else {
+                    if (s->isgrid) {
+                        nz = 1.0 / (Etotal * c.unitinmm * c.unitinmm * c.unitinmm);
+                    } else if (basis1) {
+                        nz = Eabsorb / (Etotal * dep[j] * 0.25f);
+                    } else {
+                        nz = Eabsorb / (Etotal * dep[j]);
+                    }
+
+                    if (c.outputtype == MMCB_OT_FLUX) {
+                        nz /= c.tstep;
+                    }
+                }
+
+                fac[j] = nz;
+                sum += nz;
+            }
+
+            out->normalizer = sum / srcnum;
+            const bool divide = needdep && basis0;
+            CUK(mmcb_k_norm_scale(d_src, d_out, n, datalen, srcnum, divide ? d_evol : NULL, divide ? d_emua : NULL, fac, s->stream));
+            d_src = d_out;
+
+            if (c.issaveref && !dref.empty()) {          // :2160-2167
+                const float nz = 1.f / (float)out->energytot[0];
+
+                for (size_t i = 0; i < dref.size(); i++) {
+                    dref[i] *= nz;
+                }
+            }
+
+            for (void* q : {(void*)d_dep, (void*)d_evol, (void*)d_emua, (void*)d_nvol}) {
+                if (q) {
+                    cudaFreeAsync(q, s->stream);
+                }
+            }
+        }
+
+        tr.mark("fetch: normalise (device)");
+
+        if (out->overwrite) {
+            CU(cudaMemcpyAsync(out->field, d_src, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+        } else {
+            std::vector<double> W(n);
+            CU(cudaMemcpyAsync(W.data(), d_src, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+
+            for (size_t i = 0; i < n; i++) {
+                out->field[i] += W[i];          // cfg->exportfield[i] += field[i]  (src/mmc_cu_host.cu:918-920)
+            }
+        }
+
+        if (d_out) {
+            cudaFreeAsync(d_out, s->stream);
+        }
+
+        tr.mark("fetch: volume D2H");
+    } else if (out->field) {
         // raw sums -> double on the device (and elem->node spreading for nodal output), then one D2H copy per volume
         const bool nodal = (!s->isgrid && !s->ishp && c.basisorder);
         const int nslots = s->cfg.nslots;
@@ -2058,12 +2202,12 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
         }
 
         for (size_t i = 0; i < s->fieldlen; i++) {
-            out->field[i] += W[i];          // cfg->exportfield[i] += field[i]  (src/mmc_cu_host.cu:918-920)
+            out->field[i] = (out->overwrite ? 0.0 : out->field[i]) + W[i];          // cfg->exportfield[i] += field[i]  (src/mmc_cu_host.cu:918-920)
         }
 
         if (out->field_im && !Wim.empty()) {
             for (size_t i = 0; i < s->fieldlen; i++) {
-                out->field_im[i] += Wim[i];
+                out->field_im[i] = (out->overwrite ? 0.0 : out->field_im[i]) + Wim[i];
             }
         }
 
@@ -2162,7 +2306,7 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
 
     if (out->dref && !dref.empty()) {
         for (size_t i = 0; i < dref.size(); i++) {
-            out->dref[i] += dref[i];
+            out->dref[i] = (out->overwrite ? 0.0 : out->dref[i]) + dref[i];
         }
     }
 

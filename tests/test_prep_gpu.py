@@ -63,3 +63,31 @@ def test_device_prep_gives_the_same_simulation():
     assert a["raytet"] == b["raytet"]
     assert a["energyesc"][0] == b["energyesc"][0]
     np.testing.assert_allclose(a["raw"], b["raw"], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("name", ["blb_elem_reflect", "blb_nodal_reflect", "grid_1mm", "havel_nodal", "plucker_elem", "blb_energy", "blb_fluence",
+                                  "pattern_share2", "blb_dref"])
+def test_device_normalisation_equals_host_normalisation(name):
+    """mesh_normalize (src/mmc_mesh.c:2154-2279) on the device (mmcb_adjoint.cu: mmcb_norm_*) against the host restatement of the same
+    function kept in mmcb_host.cu, on identical raw volumes (static schedule, same seeds).  The reductions run in a different order:
+    rtol 1e-10."""
+    import test_gpu_parity as tp
+    node, elem, et, med = cases.case_mesh(name)
+    kw = cases.case_kwargs(name)
+    kw.update(nphoton=20000, schedule=1, hotcache=-1, isnormalized=1)
+    cfg = tp._cfg(node, elem, et, med, **kw)
+    a = mmc.run(cfg)
+    os.environ["MMCB_HOST_NORM"] = "1"
+    try:
+        b = mmc.run(cfg)
+    finally:
+        del os.environ["MMCB_HOST_NORM"]
+    assert a["raytet"] == b["raytet"]
+    np.testing.assert_allclose(a["normalizer"], b["normalizer"], rtol=1e-10)
+    fa, fb = a["raw"], b["raw"]
+    assert np.array_equal(np.isfinite(fa), np.isfinite(fb))
+    ok = np.isfinite(fb)
+    np.testing.assert_allclose(fa[ok], fb[ok], rtol=1e-10, atol=0)
+    assert np.abs(fb[ok]).max() > 0
+    if "dref" in b:
+        np.testing.assert_allclose(a["dref"], b["dref"], rtol=1e-12)
