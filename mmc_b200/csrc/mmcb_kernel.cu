@@ -1147,8 +1147,12 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 int seg = ((int)(Lmove * gp.dstep) + 1) << 1;
                 float seglen = Lmove / seg;
                 float segdecay = __expf(-prop.x * seglen);
-                float dx = p.vx * seglen, dy = p.vy * seglen, dz = p.vz * seglen;
-                float sx = (p.px - gp.nmin[0]) + dx * 0.5f, sy = (p.py - gp.nmin[1]) + dy * 0.5f, sz = (p.pz - gp.nmin[2]) + dz * 0.5f;
+                // segment midpoints in voxel units: g = ((p - nmin) + (k + 1/2) v seglen) / step, index = max(floor(g), 0) like the
+                // reference's `(S.x > 0) ? __float2int_rd(S.x * dstep) : 0` (:1056-1058)
+                const float vs = seglen * gp.dstep;
+                float dx = p.vx * vs, dy = p.vy * vs, dz = p.vz * vs;
+                float sx = (p.px - gp.nmin[0]) * gp.dstep + dx * 0.5f, sy = (p.py - gp.nmin[1]) * gp.dstep + dy * 0.5f,
+                      sz = (p.pz - gp.nmin[2]) * gp.dstep + dz * 0.5f;
                 float frac = (totalloss == 0.f) ? 0.f : (1.f - segdecay) / totalloss;
                 float segw = ww;
                 float seg_re = currweight, seg_im = p.w_im, dsn = 0.f, dcs = 1.f;
@@ -1159,18 +1163,14 @@ mmcb_photon_kernel(const mmcb_kargs a) {
 
                 // consecutive segments in one voxel are merged before they reach the volume (the reference issues one atomic
                 // per segment once the photon is about to leave the element, src/mmc_core.cl:1150-1206): same sums, fewer
-                // atomics.  Pass k == seg is the closing flush, so the loop holds the only deposit site of this branch.
-                for (int k = 0; k <= seg; k++) {
-                    unsigned int newidx;
+                // atomics.  The loop body is one segment; the run that is still open when the photon leaves the element (or runs
+                // out of time) is closed after the loop.
+                const unsigned int cx = gp.crop0[0], cy = gp.crop0[1];
+                #pragma unroll 2
 
-                    if (k < seg) {
-                        const int ix = (sx > 0.f) ? __float2int_rd(sx * gp.dstep) : 0;
-                        const int iy = (sy > 0.f) ? __float2int_rd(sy * gp.dstep) : 0;
-                        const int iz = (sz > 0.f) ? __float2int_rd(sz * gp.dstep) : 0;
-                        newidx = (unsigned int)(iz * gp.crop0[1] + iy * gp.crop0[0] + ix) + tshift;
-                    } else {
-                        newidx = flushnow ? 0xFFFFFFFFu : p.oldidx;
-                    }
+                for (int k = 0; k < seg; k++) {
+                    const int ix = max(__float2int_rd(sx), 0), iy = max(__float2int_rd(sy), 0), iz = max(__float2int_rd(sz), 0);
+                    const unsigned int newidx = (unsigned int)iz * cy + (unsigned int)iy * cx + (unsigned int)ix + tshift;
 
                     if (newidx != p.oldidx) {
                         if (RF ? (p.oldidx != 0xFFFFFFFFu) : (p.oldw > 0.f)) {      // RF: ungated like :1084-1112
@@ -1186,23 +1186,35 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                         p.oldw_im = 0.f;
                     }
 
-                    if (k < seg) {
-                        if constexpr (RF) {
-                            const float w0r = seg_re, w0i = seg_im;
-                            seg_re = segdecay * (w0r * dcs + w0i * dsn);
-                            seg_im = segdecay * (-w0r * dsn + w0i * dcs);
-                            const float dr = w0r - seg_re, di = w0i - seg_im;
-                            p.oldw += (a_mag2 < EPS) ? (w0r * segw) : __fdividef(dr * prop.x + di * a_im, a_mag2);
-                            p.oldw_im += (a_mag2 < EPS) ? (w0i * segw) : __fdividef(di * prop.x - dr * a_im, a_mag2);
-                        } else {
-                            p.oldw += segw * frac;
-                        }
-
-                        segw *= segdecay;
-                        sx += dx;
-                        sy += dy;
-                        sz += dz;
+                    if constexpr (RF) {
+                        const float w0r = seg_re, w0i = seg_im;
+                        seg_re = segdecay * (w0r * dcs + w0i * dsn);
+                        seg_im = segdecay * (-w0r * dsn + w0i * dcs);
+                        const float dr = w0r - seg_re, di = w0i - seg_im;
+                        p.oldw += (a_mag2 < EPS) ? (w0r * segw) : __fdividef(dr * prop.x + di * a_im, a_mag2);
+                        p.oldw_im += (a_mag2 < EPS) ? (w0i * segw) : __fdividef(di * prop.x - dr * a_im, a_mag2);
+                    } else {
+                        p.oldw += segw * frac;
                     }
+
+                    segw *= segdecay;
+                    sx += dx;
+                    sy += dy;
+                    sz += dz;
+                }
+
+                if (flushnow) {
+                    if (RF ? (p.oldidx != 0xFFFFFFFFu) : (p.oldw > 0.f)) {
+                        flush_deposit<GENERAL>(gfield, p.oldidx, p.oldw, p, a, hot);
+
+                        if constexpr (RF) {
+                            red_global(gfield_im + (unsigned long long)p.oldidx * sizeof(acc_t), p.oldw_im, (acc_t*)0);
+                        }
+                    }
+
+                    p.oldidx = 0xFFFFFFFFu;
+                    p.oldw = 0.f;
+                    p.oldw_im = 0.f;
                 }
 
                 if constexpr (RF) {                         // :1209-1212
