@@ -826,6 +826,11 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
 // enum TRTMethod, src/mmc_utils.h); DET: detected-photon records;
 // GENERAL: area sources, photon sharing, replay, trajectories, diffuse reflectance.
 // ----------------------------------------------------------------------------------------------------
+#ifndef MMCB_GRID_UNROLL
+#define MMCB_GRID_UNROLL 2      // segment loop of the dual-grid deposit (measured: profiles/)
+#endif
+#define MMCB_PRAGMA_(x) _Pragma(#x)
+#define MMCB_UNROLL(n) MMCB_PRAGMA_(unroll n)
 #ifndef MMCB_MAXTHREADS
 #define MMCB_MAXTHREADS 128
 #endif
@@ -1166,7 +1171,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 // atomics.  The loop body is one segment; the run that is still open when the photon leaves the element (or runs
                 // out of time) is closed after the loop.
                 const unsigned int cx = gp.crop0[0], cy = gp.crop0[1];
-                #pragma unroll 2
+                MMCB_UNROLL(MMCB_GRID_UNROLL)
 
                 for (int k = 0; k < seg; k++) {
                     const int ix = max(__float2int_rd(sx), 0), iy = max(__float2int_rd(sy), 0), iz = max(__float2int_rd(sz), 0);

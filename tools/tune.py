@@ -11,11 +11,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "build", "variants")
 VARIANTS = {
-    "b128_m8": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=8"],
-    "b128_m8_pf": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=8", "-DMMCB_PREFETCH"],
-    "b128_m6": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=6"],
-    "b128_m6_pf": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=6", "-DMMCB_PREFETCH"],
-    "b256_m4": ["-DMMCB_MAXTHREADS=256", "-DMMCB_MINBLOCKS=4"],
+    "b128_u1": ["-DMMCB_GRID_UNROLL=1"],
+    "b128_u2": ["-DMMCB_GRID_UNROLL=2"],
+    "b128_u4": ["-DMMCB_GRID_UNROLL=4"],
 }
 
 
