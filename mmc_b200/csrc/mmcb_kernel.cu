@@ -483,7 +483,8 @@ __device__ __forceinline__ void reflectray(Photon& p, int& neweid, float nx, flo
 extern __shared__ float4 smem4[];
 
 __device__ __forceinline__ void red_global(unsigned long long gaddr, float v, double*) {
-    asm volatile("red.global.add.f64 [%0], %1;" :: "l"(gaddr), "d"((double)v) : "memory");
+    // the widening is spelled in PTX: under -use_fast_math the C++ cast becomes cvt.ftz, which costs an extra FMUL.FTZ x1 per deposit
+    asm volatile("{\n\t.reg .f64 d;\n\tcvt.f64.f32 d, %1;\n\tred.global.add.f64 [%0], d;\n\t}" :: "l"(gaddr), "f"(v) : "memory");
 }
 __device__ __forceinline__ void red_global(unsigned long long gaddr, float v, float*) {
     asm volatile("red.global.add.f32 [%0], %1;" :: "l"(gaddr), "f"(v) : "memory");
@@ -492,13 +493,15 @@ __device__ __forceinline__ void red_global(unsigned long long gaddr, float v, fl
 // deposit of a merged run (single source or photon-sharing patterns), src/mmc_core.cl:902-946.  gfield: global-space address
 // of the accumulator volume.
 template <bool GENERAL>
-__device__ __forceinline__ void flush_deposit(unsigned long long gfield, unsigned int idx, float w, const Photon& p, const mmcb_kargs& a, bool hot) {
+__device__ __forceinline__ void flush_deposit(unsigned long long gfield, unsigned int idx, float w, const Photon& p, const mmcb_kargs& a, const uint2 hot) {
 #ifdef MMCB_COUNT_DEPOSITS      // analysis build (tools/hotspots.py): the volume counts the atomics that reach the L2
     w = 1.f;
 #endif
 
     if (!GENERAL || gp.srcnum == 1) {
-        if (hot) {          // CTA-private sum for the hottest 128-byte lines (see mmcb_types.h)
+        // CTA-private sums for the hottest 128-byte lines (see mmcb_types.h).  hot = {first index, span} of the cached groups: one
+        // unsigned compare sends every deposit outside that window (other gates, other regions) straight to the volume
+        if ((idx - hot.x) < hot.y) {
             const unsigned int* hkeys = (const unsigned int*)smem4;
             float* hvals = (float*)smem4 + MMCB_HOT_SLOTS;
             const unsigned int g = idx >> MMCB_HOT_GROUP_LOG2, h = MMCB_HOT_HASH(g);
@@ -588,7 +591,7 @@ __device__ __forceinline__ float4 launch_bary(const Photon& p, const mmcb_kargs&
 }
 
 template <int METHOD, bool GENERAL>
-__device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kargs& a, const float4* smed, unsigned long long gfield, bool hot,
+__device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kargs& a, const float4* smed, unsigned long long gfield, const uint2 hot,
                                         bool& found, float& Lmove, bool& isend, bool& timeup, int& neweid, float& fnx, float& fny, float& fnz,
                                         int& type, unsigned& flags, float4& prop) {
     const mmcb_tetrec_big* rec = a.tetbig + (p.eid - 1);
@@ -846,7 +849,8 @@ mmcb_photon_kernel(const mmcb_kargs a) {
     static_assert(!RF || (GENERAL && METHOD >= 3), "RF forward runs use the general branch-less Badouel kernels");
     constexpr bool GRID = (METHOD == 4);
     constexpr bool HP = (METHOD <= 1);          // Havel / Plucker: 256-byte records, CPU-file semantics (src/mmc_raytrace.c)
-    const bool hot = gp.hotcache != 0 && a.hotstat[MMCB_HOT_STAT_USEFUL] != 0;
+    const bool hoton = gp.hotcache != 0 && a.hotstat[MMCB_HOT_STAT_USEFUL] != 0;
+    const uint2 hot = hoton ? make_uint2(a.hotstat[MMCB_HOT_STAT_LO], a.hotstat[MMCB_HOT_STAT_SPAN]) : make_uint2(0u, 0u);
     unsigned int* hkeys = (unsigned int*)smem4;
     float* hvals = (float*)smem4 + MMCB_HOT_SLOTS;
     float4* smed = smem4 + (gp.hotcache ? MMCB_HOT_BYTES / 16 : 0);     // media table, gp.nmedia entries
@@ -862,7 +866,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
         smed[i] = a.med[i];
     }
 
-    if (hot) {
+    if (hoton) {
         for (int i = threadIdx.x; i < MMCB_HOT_SLOTS; i += blockDim.x) {
             hkeys[i] = a.hotkeys[i];
         }
@@ -1420,7 +1424,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
     // the stream state goes back in the seed-word packing: the next launch of the session may continue the streams
     *(uint4*)(a.seeds + 4 * (size_t)tid) = make_uint4((unsigned int)(rng.t0 >> 32), (unsigned int)rng.t0, (unsigned int)(rng.t1 >> 32), (unsigned int)rng.t1);
 
-    if (hot) {              // flush the CTA-private sums of the hot lines
+    if (hoton) {            // flush the CTA-private sums of the hot lines
         __syncthreads();
 
         for (int i = threadIdx.x; i < MMCB_HOT_SLOTS * MMCB_HOT_GROUP; i += blockDim.x) {
@@ -1625,7 +1629,19 @@ __global__ void mmcb_hot_build_kernel(const uint2* __restrict__ cand, unsigned i
 
     if (threadIdx.x == 0) {     // one line serialises the kernel only when it draws a sizeable share of all deposits
         const float mx = __uint_as_float(stat[0]), tot = __uint_as_float(stat[MMCB_HOT_STAT_TOTAL]);
-        stat[MMCB_HOT_STAT_USEFUL] = (n > 0 && tot > 0.f && mx > minshare * tot) ? 1u : 0u;
+        unsigned int lo = 0xFFFFFFFFu, hi = 0;
+
+        for (int i = 0; i < MMCB_HOT_SLOTS; i++) {
+            if (k[i] != MMCB_HOT_EMPTY) {
+                lo = min(lo, k[i]);
+                hi = max(hi, k[i]);
+            }
+        }
+
+        const bool useful = (n > 0 && lo <= hi && tot > 0.f && mx > minshare * tot);
+        stat[MMCB_HOT_STAT_USEFUL] = useful ? 1u : 0u;
+        stat[MMCB_HOT_STAT_LO] = useful ? (lo << MMCB_HOT_GROUP_LOG2) : 0u;             // window of accumulator indices that can hit the cache
+        stat[MMCB_HOT_STAT_SPAN] = useful ? ((hi - lo + 1u) << MMCB_HOT_GROUP_LOG2) : 0u;
     }
 }
 

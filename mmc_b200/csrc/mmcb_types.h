@@ -13,15 +13,17 @@
 #define MMCB_HOT_GROUP_LOG2 4       // accumulators per cached group
 #define MMCB_HOT_GROUP    (1 << MMCB_HOT_GROUP_LOG2)
 #ifndef MMCB_HOT_SLOTS_LOG2
-#define MMCB_HOT_SLOTS_LOG2 6       // direct-mapped slots per CTA (64 x 16 floats = 4 KB + 256 B of keys): the few hottest lines are what
-#endif                              // matters (measured: 64, 128 and 256 slots run the same, profiles/)
+#define MMCB_HOT_SLOTS_LOG2 4       // direct-mapped slots per CTA (16 x 16 floats = 1 KB + 64 B of keys): the few hottest lines are what
+#endif                              // matters (measured: 4 to 256 slots run within 3 %, profiles/r1h_tune_hotslots.jsonl)
 #define MMCB_HOT_SLOTS    (1 << MMCB_HOT_SLOTS_LOG2)
 #define MMCB_HOT_EMPTY    0xFFFFFFFFu
 // selection scratch (unsigned int words): [0] bits of the largest group sum, [1] candidate count, [2..33] histogram of the
 // exponent distance to the maximum, [34] bits of the total deposited weight (float), [35] 1 when the cache is worth its lookups
-#define MMCB_HOT_STAT_WORDS 36
+#define MMCB_HOT_STAT_WORDS 38
 #define MMCB_HOT_STAT_TOTAL 34
 #define MMCB_HOT_STAT_USEFUL 35
+#define MMCB_HOT_STAT_LO   36     // first accumulator index of the window spanned by the cached groups
+#define MMCB_HOT_STAT_SPAN 37     // its length (0: cache off)
 #define MMCB_HOT_HASH(g)  (((g) * 0x9E3779B1u) >> (32 - MMCB_HOT_SLOTS_LOG2))
 
 // One tetrahedron = one 96-byte record, 32-byte aligned: three 256-bit gathers (LDG.E.256) bring everything a
