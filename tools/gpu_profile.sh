@@ -14,9 +14,9 @@ MMCB_TRACE=1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 
 # launch list of the default bench command (cold-cache, serialised: shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > $O/ncu_launch_${TAG}.log 2>&1
-# full captures (1e6 photons keeps the ~40 replays short)
+# full captures at the benched photon count (about 40 replays of a 30-170 ms kernel)
 ncu --set full --clock-control none --import-source on -k regex:mmcb_photon -s 1 -c 1 -f -o $O/prof_grid_${TAG} \
-    python bench.py --steps 1 --warmup 1 --photons 1e6 --no-cpu-baseline --no-e2e > $O/ncu_grid_${TAG}.log 2>&1
+    python bench.py --steps 1 --warmup 1 --photons 1e7 --no-cpu-baseline --no-e2e > $O/ncu_grid_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:mmcb_photon -s 1 -c 1 -f -o $O/prof_elem_${TAG} \
-    python bench.py --workload cube60 --method elem --steps 1 --warmup 1 --photons 1e6 --no-cpu-baseline --no-e2e > $O/ncu_elem_${TAG}.log 2>&1
+    python bench.py --workload cube60 --method elem --steps 1 --warmup 1 --photons 1e7 --no-cpu-baseline --no-e2e > $O/ncu_elem_${TAG}.log 2>&1
 ls -la $O
