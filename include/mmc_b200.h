@@ -179,6 +179,7 @@ typedef struct mmcb_devptrs {
     float*  detected;   unsigned int* detcount;  int reclen;
     uint64_t* detseed;
     double* dref;       size_t dreflen;
+    void*  field_im;    /* RF runs: imaginary accumulator volume, same length and type as `field`; NULL otherwise */
 } mmcb_devptrs;
 
 /* ---- library info ------------------------------------------------------------------------------- */

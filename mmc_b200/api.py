@@ -95,7 +95,7 @@ class DevPtrs(C.Structure):
     _fields_ = [("field", C.c_void_p), ("fieldlen", C.c_size_t), ("field_is_double", C.c_int),
                 ("energy", C.c_void_p), ("raytet", C.c_void_p),
                 ("detected", C.c_void_p), ("detcount", C.c_void_p), ("reclen", C.c_int),
-                ("detseed", C.c_void_p), ("dref", C.c_void_p), ("dreflen", C.c_size_t)]
+                ("detseed", C.c_void_p), ("dref", C.c_void_p), ("dreflen", C.c_size_t), ("field_im", C.c_void_p)]
 
 
 EXPORTS = ["mmcb_version", "mmcb_last_error", "mmcb_list_gpu", "mmcb_query_sizes", "mmcb_run_simulation",

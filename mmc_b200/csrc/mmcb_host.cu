@@ -21,7 +21,8 @@
 
 // kernel-side launchers (mmcb_kernel.cu)
 extern "C" int mmcb_k_upload_param(const mmcb_kparam* hp, const float* det4, int detnum, cudaStream_t st);
-extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int method, int isdet, int isgeneral, int isrf, cudaStream_t st);
+extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int carveout,
+                                     cudaStream_t st);
 extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int* blocks_per_sm);
 // mesh pre-processing on the device (mmcb_prep.cu)
 extern "C" int mmcb_k_facenb(const int* d_elem, int ne, int* d_facenb, cudaStream_t st);
@@ -946,6 +947,7 @@ struct mmcb_session {
     PrepMesh mesh;
     mmcb_kparam kp, kp_pilot;
     size_t smem_scout = 0;         // shared memory of the scout launch (no detector columns, no cache)
+    int carveout = -1;             // preferred shared-memory carve-out (percent) of the photon kernel
     mmcb_kargs ka;
     cudaStream_t stream = NULL;
     cudaEvent_t ev0 = NULL, ev1 = NULL;
@@ -1310,6 +1312,9 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
         return fail(MMCB_ERR_CUDA, "kernel cannot be resident with block=%d smem=%zu", s->block, s->smem);
     }
 
+    // resident CTAs x (dynamic + 1 KB reserved shared memory) of the 228 KB an SM can carve out
+    s->carveout = (int)std::min<size_t>(100, ((size_t)bps * (s->smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+
     if (c.nthread > 0) {
         s->grid = std::max(1, c.nthread / s->block);
     } else {
@@ -1670,7 +1675,7 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
         ka.trajcount = ka.detcount + 1;
         CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
         CUK(mmcb_k_upload_param(&kp, s->cfg.detpos.data(), c.detnum, st));
-        CUK(mmcb_k_launch_photons(&ka, s->grid, s->block, s->smem_scout, c.method, 0, s->isgeneral, 0, st));
+        CUK(mmcb_k_launch_photons(&ka, s->grid, s->block, s->smem_scout, c.method, 0, s->isgeneral, 0, s->carveout, st));
         CUK(mmcb_k_hot_select(scr, flen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys, c.hotcache > 0 ? 0.f : MMCB_HOT_MINSHARE, st));
         CU(cudaFreeAsync(scr, st));
         s->hot_ready = true;
@@ -1693,7 +1698,7 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
         kp.hotcache = (part == 1 && s->hot_ready) ? 1 : 0;
         CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
         CUK(mmcb_k_upload_param(&kp, s->cfg.detpos.data(), c.detnum, st));
-        CUK(mmcb_k_launch_photons(&s->ka, s->grid, s->block, kp.hotcache ? s->smem : s->smem_base, c.method, s->isdet, s->isgeneral, s->cfg.isrf, st));
+        CUK(mmcb_k_launch_photons(&s->ka, s->grid, s->block, kp.hotcache ? s->smem : s->smem_base, c.method, s->isdet, s->isgeneral, s->cfg.isrf, s->carveout, st));
 
         if (part == 0) {     // the streams continue from the states the pilot wrote back (no reseeding)
             CUK(mmcb_k_hot_select(s->d_field, s->efieldlen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys,
@@ -1746,6 +1751,7 @@ int mmcb_get_devptrs(mmcb_session* s, mmcb_devptrs* p) {
     p->detseed = (uint64_t*)s->d_detseed;
     p->dref = s->d_dref;
     p->dreflen = (size_t)s->mesh.nf * s->cfg.maxgate;
+    p->field_im = s->d_field_im;
     return 0;
 }
 

@@ -26,7 +26,9 @@ def split_photons(nphoton, workload):
 def reduce_results(local, dist, device="cpu", dst=0):
     """Sum-reduce field/energy/raytet to rank `dst`, gather detected-photon rows (counts first, then padded payload)
     and truncate at maxdetphoton like the reference (src/mmc_cu_host.cu:823-834).  `local` is a dict with numpy (or
-    torch) entries: field, energytot, energyesc, raytet, detp [n,reclen] (optional), seeds [n,2] (optional)."""
+    torch) entries: field, energytot, energyesc, raytet, field_im (optional, RF), detp [n,reclen] (optional), seeds [n,2] (optional).
+    Adjoint Jacobians are products of slot fluences: reduce the raw volumes first (in place, through mmcb_set_field_buffer /
+    mmcb_get_devptrs), then let rank `dst` fetch -- mmcb_fetch normalises and runs the post-kernels on the reduced volumes."""
     import torch
 
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -41,8 +43,14 @@ def reduce_results(local, dist, device="cpu", dst=0):
     scal = T(np.concatenate([np.atleast_1d(local["energytot"]), np.atleast_1d(local["energyesc"]), [local["raytet"]]]))
     dist.reduce(scal, dst=dst, op=dist.ReduceOp.SUM)
     ns = (len(scal) - 1) // 2
+    field_im = None
+    if local.get("field_im") is not None:       # RF runs: the imaginary volume is reduced like the real one
+        field_im = T(local["field_im"])
+        dist.reduce(field_im, dst=dst, op=dist.ReduceOp.SUM)
     if rank == dst:
         out["field"] = field
+        if field_im is not None:
+            out["field_im"] = field_im
         out["energytot"] = scal[:ns].cpu().numpy()
         out["energyesc"] = scal[ns:2 * ns].cpu().numpy()
         out["raytet"] = float(scal[-1])
