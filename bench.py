@@ -233,7 +233,9 @@ def main():
                 stream.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            sess.launch(nphoton, photon_offset=0, seed=cfg["seed"], seed_offset=rank + world * i, stream=stream.cuda_stream)
+            # every rank draws consecutive slices of ITS OWN host stream (srand(seed + 7919 rank)): interleaving the ranks' slices in one
+            # stream makes each rank generate and discard the other ranks' words (17 ms per step at 8 ranks)
+            sess.launch(nphoton, photon_offset=0, seed=cfg["seed"] + 7919 * rank, seed_offset=i, stream=stream.cuda_stream)
             if dist is not None:
                 dist.reduce(field, dst=0, op=dist.ReduceOp.SUM)
             e1.record(stream)

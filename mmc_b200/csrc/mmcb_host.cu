@@ -985,7 +985,10 @@ struct mmcb_session {
     uint2* d_hotcand = NULL;
     bool hot_allowed = false, hot_ready = false;
     size_t smem_base = 0;
-    std::vector<uint32_t> hseeds;
+    std::vector<uint32_t> hseeds, hseeds_next;     // this launch's seed words / the next slice, drawn ahead
+    bool next_valid = false;
+    int next_seed = 0;
+    size_t next_start = 0;
     // host seed stream position: consecutive slices (ranks/respins/bench steps) continue instead of replaying rand() from 0
     GlibcRand* seedgen = NULL;
     int seedgen_seed = 0;
@@ -1616,22 +1619,28 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
     {
         const size_t skip = (size_t)seed_offset * 4 * (size_t)s->nthread;
 
-        if (!s->seedgen || s->seedgen_seed != seed || s->seedgen_pos > skip) {
-            delete s->seedgen;
-            s->seedgen = new GlibcRand((unsigned int)seed);
-            s->seedgen_seed = seed;
-            s->seedgen_pos = 0;
+        if (s->next_valid && s->next_seed == seed && s->next_start == skip && s->hseeds_next.size() == s->hseeds.size()) {
+            s->hseeds.swap(s->hseeds_next);     // generated while the previous launch was running (below)
+        } else {
+            if (!s->seedgen || s->seedgen_seed != seed || s->seedgen_pos > skip) {
+                delete s->seedgen;
+                s->seedgen = new GlibcRand((unsigned int)seed);
+                s->seedgen_seed = seed;
+                s->seedgen_pos = 0;
+            }
+
+            for (; s->seedgen_pos < skip; s->seedgen_pos++) {
+                s->seedgen->next();
+            }
+
+            for (size_t i = 0; i < s->hseeds.size(); i++) {
+                s->hseeds[i] = s->seedgen->next();
+            }
+
+            s->seedgen_pos += s->hseeds.size();
         }
 
-        for (; s->seedgen_pos < skip; s->seedgen_pos++) {
-            s->seedgen->next();
-        }
-
-        for (size_t i = 0; i < s->hseeds.size(); i++) {
-            s->hseeds[i] = s->seedgen->next();
-        }
-
-        s->seedgen_pos += s->hseeds.size();
+        s->next_valid = false;
     }
 
     CU(cudaMemcpyAsync(s->d_seeds, s->hseeds.data(), s->hseeds.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
@@ -1709,6 +1718,22 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
 
     CU(cudaEventRecord(s->ev1, st));
     s->launched += nphoton;
+
+    // the kernel is running: draw the next slice of the host stream now (respin, bench steps and ranks with their own seed ask for
+    // consecutive slices), so that the next launch does not start with ~2 ms of rand() on the critical path
+    if (s->seedgen && s->seedgen_seed == seed) {
+        s->hseeds_next.resize(s->hseeds.size());
+        s->next_start = s->seedgen_pos;
+
+        for (size_t i = 0; i < s->hseeds_next.size(); i++) {
+            s->hseeds_next[i] = s->seedgen->next();
+        }
+
+        s->seedgen_pos += s->hseeds_next.size();
+        s->next_seed = seed;
+        s->next_valid = true;
+    }
+
     return 0;
 }
 
