@@ -597,31 +597,104 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
                                         int& type, unsigned& flags, float4& prop) {
     const mmcb_tetrec_big* rec = a.tetbig + (p.eid - 1);
     float tail[8];              // nb[4] node[4]
-    ld256(rec->nb, tail);
-    const int2 tf = *(const int2*)&rec->type;
+    int2 tf;
+    float r0[8], r1[8];         // Havel: face planes from the 96-byte record (same normals and offsets as tab[12 i .. 12 i + 3])
+
+    if constexpr (METHOD == 1) {
+        // the plane tests, neighbours, label and flags come from the compact record the BLB kernels use (3 x 256-bit, 13 MB for
+        // cube60 instead of 34 MB of 256-byte records); the big record supplies only the edge vectors of ONE face and, for nodal
+        // output, the node ids
+        const mmcb_tetrec* srec = a.tet + (p.eid - 1);
+        float r2[8];
+        ld256(srec, r0);
+        ld256((const char*)srec + 32, r1);
+        ld256((const char*)srec + 64, r2);
+        tail[0] = r2[0];
+        tail[1] = r2[1];
+        tail[2] = r2[2];
+        tail[3] = r2[3];
+        tf = make_int2(__float_as_int(r2[4]), __float_as_int(r2[5]));
+        tail[4] = tail[5] = tail[6] = tail[7] = 0.f;
+
+        if (gp.basisorder) {
+            float nd4[4];
+            ld128(rec->node, nd4);
+            tail[4] = nd4[0];
+            tail[5] = nd4[1];
+            tail[6] = nd4[2];
+            tail[7] = nd4[3];
+        }
+    } else {
+        ld256(rec->nb, tail);
+        tf = *(const int2*)&rec->type;
+    }
+
     type = tf.x;
     int fi = -1;                // tracer face 0..3
     float Lp0 = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
     float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;      // barycentric coordinates of the exit point (local node order)
 
     if constexpr (METHOD == 1) {
-        // ---- Havel: first face (in order) with det >= 0, 0 <= t <= 1e10, and the hit inside the triangle
+        // ---- Havel: first face (in order) with det >= 0, 0 <= t <= 1e10, and the hit inside the triangle (havel_sse4, :531-561).
+        // For a ray that starts inside the element exactly one face passes all three tests, and it is the one with the smallest t.
+        // So: the four plane tests first (4 loads), the two edge tests for the nearest face only (2 loads); the sequential search of
+        // the reference (12 loads) runs only when that face fails its edge tests (origin on an edge / outside after drift).
         float tu = 0.f, tv = 0.f;
-        #pragma unroll
+        {
+            float tt[4], dets[4], detts[4];
+            #pragma unroll
 
-        for (int i = 0; i < 4; i++) {
-            float n[4], e1[4], e2[4];
-            ld128(rec->tab + 12 * i, n);
-            ld128(rec->tab + 12 * i + 4, e1);
-            ld128(rec->tab + 12 * i + 8, e2);
+            for (int i = 0; i < 4; i++) {       // n = (r0[i], r0[4+i], r1[i]), offset r1[4+i]
+                dets[i] = r0[i] * p.vx + r0[4 + i] * p.vy + r1[i] * p.vz;
+                detts[i] = (-r0[i] * p.px + -r0[4 + i] * p.py) + (-r1[i] * p.pz + r1[4 + i]);
+                const bool ok = !(__float_as_uint(dets[i]) & 0x80000000u) && samesign(detts[i], 1e10f * dets[i] - detts[i]);
+                const float t = __fdividef(detts[i], dets[i]);
+                tt[i] = (ok && t == t) ? t : 3.0e38f;
+            }
 
-            if (fi < 0) {
+            const float tmin = fminf(fminf(tt[0], tt[1]), fminf(tt[2], tt[3]));
+
+            if (tmin < 3.0e38f) {
+                const int c = (tt[0] == tmin) ? 0 : ((tt[1] == tmin) ? 1 : ((tt[2] == tmin) ? 2 : 3));
+                const float det = sel4(dets, c), dett = sel4(detts, c);
+                float e1[4], e2[4];
+                ld128(rec->tab + 12 * c + 4, e1);
+                ld128(rec->tab + 12 * c + 8, e2);
+                const float qx = p.px * det + dett * p.vx, qy = p.py * det + dett * p.vy, qz = p.pz * det + dett * p.vz;   // w = det
+                const float detu = (qx * e1[0] + qy * e1[1]) + (qz * e1[2] + det * e1[3]);
+                const float detv = (qx * e2[0] + qy * e2[1]) + (qz * e2[2] + det * e2[3]);
+
+                if (samesign(detu, det - detu) && samesign(detv, det - (detu + detv))) {
+                    const float inv = 1.f / det;
+                    const float t = dett * inv;
+
+                    if (t == t) {
+                        fi = c;
+                        Lp0 = t;
+                        tu = detu * inv;
+                        tv = detv * inv;
+                        fnx = sel4(r0, c);
+                        fny = sel4(r0 + 4, c);
+                        fnz = sel4(r1, c);
+                    }
+                }
+            }
+        }
+
+        if (fi < 0) {       // rare: the reference's sequential search, face by face
+            #pragma unroll 1
+
+            for (int i = 0; i < 4 && fi < 0; i++) {
+                float n[4], e1[4], e2[4];
+                ld128(rec->tab + 12 * i, n);
                 const float det = n[0] * p.vx + n[1] * p.vy + n[2] * p.vz;
 
                 if (!(__float_as_uint(det) & 0x80000000u)) {
                     const float dett = (-n[0] * p.px + -n[1] * p.py) + (-n[2] * p.pz + n[3]);
 
                     if (samesign(dett, 1e10f * det - dett)) {
+                        ld128(rec->tab + 12 * i + 4, e1);
+                        ld128(rec->tab + 12 * i + 8, e2);
                         const float qx = p.px * det + dett * p.vx, qy = p.py * det + dett * p.vy, qz = p.pz * det + dett * p.vz;   // w = det
                         const float detu = (qx * e1[0] + qy * e1[1]) + (qz * e1[2] + det * e1[3]);
 
@@ -659,12 +732,23 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
         const float cx = p.py * (p.pz + p.vz) - p.pz * (p.py + p.vy);
         const float cy = p.pz * (p.px + p.vx) - p.px * (p.pz + p.vz);
         const float cz = p.px * (p.py + p.vy) - p.py * (p.px + p.vx);
-        float w[6];
+        float w[6], dm[36];                  // tab: d[6][3] then m[6][3], fetched as nine 128-bit loads
         #pragma unroll
 
-        for (int i = 0; i < 6; i++) {        // tab: d[6][3] then m[6][3]
-            const float* D = rec->tab + 3 * i, *Mv = rec->tab + 18 + 3 * i;
-            w[i] = (p.vx * __ldg(Mv) + p.vy * __ldg(Mv + 1) + p.vz * __ldg(Mv + 2)) + (cx * __ldg(D) + cy * __ldg(D + 1) + cz * __ldg(D + 2));
+        for (int i = 0; i < 9; i++) {
+            float q4[4];
+            ld128(rec->tab + 4 * i, q4);
+            dm[4 * i] = q4[0];
+            dm[4 * i + 1] = q4[1];
+            dm[4 * i + 2] = q4[2];
+            dm[4 * i + 3] = q4[3];
+        }
+
+        #pragma unroll
+
+        for (int i = 0; i < 6; i++) {
+            const float* D = dm + 3 * i, *Mv = dm + 18 + 3 * i;
+            w[i] = (p.vx * Mv[0] + p.vy * Mv[1] + p.vz * Mv[2]) + (cx * D[0] + cy * D[1] + cz * D[2]);
         }
 
         // fc = {{0,4,2},{3,5,4},{2,5,1},{1,3,0}}; faces 2 and 3 negate their middle edge first (:299-301)
@@ -788,7 +872,21 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
     const unsigned int tshift = (unsigned int)gate * gp.framelen + (GENERAL ? p.slotoff : 0u);
 
     if (!nodal) {
-        flush_deposit<GENERAL>(gfield, (unsigned int)(p.eid - 1) + tshift, ww, p, a, hot);
+        // the reference adds every step to the volume (:413, :753); consecutive steps in one element and gate are summed in a
+        // register first (same total, one atomic per visit).  The run is closed when the photon leaves the element, runs out of
+        // time, or ends (main loop), so nothing is dropped.
+        const unsigned int newidx = (unsigned int)(p.eid - 1) + tshift;
+
+        if (newidx != p.oldidx) {
+            if (p.oldw > 0.f) {
+                flush_deposit<GENERAL>(gfield, p.oldidx, p.oldw, p, a, hot);
+            }
+
+            p.oldidx = newidx;
+            p.oldw = 0.f;
+        }
+
+        p.oldw += ww;
         return;
     }
 
@@ -842,7 +940,7 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
 #define MMCB_MINBLOCKS 8
 #endif
 #ifndef MMCB_MINBLOCKS_HP
-#define MMCB_MINBLOCKS_HP 4
+#define MMCB_MINBLOCKS_HP 5      // measured: 4 -> 5 CTAs per SM +2 % (cube60) .. +8 % (sphshells), profiles/r1j_tune_hp_occupancy.jsonl
 #endif
 template <int METHOD, bool DET, bool GENERAL, bool RF = false>
 __global__ void __launch_bounds__(MMCB_MAXTHREADS, (METHOD <= 1) ? MMCB_MINBLOCKS_HP : MMCB_MINBLOCKS)
@@ -1372,8 +1470,18 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 }
             }
 
-            // a merged deposit may still be pending (photon died at a scattering site): the reference drops it only
-            // when the run ended on `isend` -- it flushes on the NEXT step, which never comes; we keep that behaviour.
+            // a merged deposit may still be pending (photon died at a scattering site): the reference GPU kernel drops it only
+            // when the run ended on `isend` -- it flushes on the NEXT step, which never comes; we keep that behaviour.  The
+            // Havel/Plucker kernels follow the CPU file, which deposits every step: their pending run is written out.
+            if constexpr (HP) {
+                if (p.oldw > 0.f) {
+                    flush_deposit<GENERAL>(gfield, p.oldidx, p.oldw, p, a, hot);
+                }
+
+                p.oldidx = 0xFFFFFFFFu;
+                p.oldw = 0.f;
+            }
+
             state = 0;
         }
         }   // state == 1

@@ -11,10 +11,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "build", "variants")
 VARIANTS = {
-    "b128_h6": ["-DMMCB_HOT_SLOTS_LOG2=6"],
-    "b128_h4": ["-DMMCB_HOT_SLOTS_LOG2=4"],
-    "b128_h3": ["-DMMCB_HOT_SLOTS_LOG2=3"],
-    "b128_h2": ["-DMMCB_HOT_SLOTS_LOG2=2"],
+    "b128_hp4": ["-DMMCB_MINBLOCKS_HP=4"],
+    "b128_hp5": ["-DMMCB_MINBLOCKS_HP=5"],
+    "b128_hp6": ["-DMMCB_MINBLOCKS_HP=6"],
 }
 
 
@@ -37,7 +36,7 @@ def main():
             continue
         block = tag.split("_")[0][1:]
         for w in wl:
-            for hot in (1,):
+            for hot in (0,):
                 name, method, nph = w.split(":")
                 env = dict(os.environ, MMCB_LIB=lib, MMCB_BLOCK=block, MMCB_HOTCACHE=str(hot))
                 r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", name, "--method", method, "--photons", nph,
