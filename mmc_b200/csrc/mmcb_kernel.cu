@@ -625,6 +625,12 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
             tail[7] = nd4[3];
         }
     } else {
+        // Plucker: the edge tables decide the exit face and give its barycentric coordinates; the exit point itself is taken on
+        // that face's plane (compact record), which is the same point as the reference's node interpolation (getinterp, :165-169)
+        // up to rounding and needs no second, dependent round trip for three node positions
+        const mmcb_tetrec* srec = a.tet + (p.eid - 1);
+        ld256(srec, r0);
+        ld256((const char*)srec + 32, r1);
         ld256(rec->nb, tail);
         tf = *(const int2*)&rec->type;
     }
@@ -773,18 +779,16 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
             b1 = (fi == 0) ? bc : ((fi == 1) ? bb : ((fi == 2) ? 0.f : ba));
             b2 = (fi == 0) ? 0.f : ((fi == 1) ? bc : ((fi == 2) ? ba : bc));
             b3 = (fi == 0) ? ba : ((fi == 1) ? ba : ((fi == 2) ? bc : 0.f));
-            // pout = sum_k b_k node_k over the three nodes of the exit face (getinterp, :165-169)
-            const int n0 = __float_as_int(tail[4]), n1 = __float_as_int(tail[5]), n2 = __float_as_int(tail[6]), n3 = __float_as_int(tail[7]);
-            const int ia = (fi == 2) ? n2 : ((fi == 3) ? n1 : n3), ib = (fi == 1) ? n1 : n0, ic = (fi == 0) ? n1 : ((fi == 2) ? n3 : n2);
-            const float* qa = a.node + 3 * (size_t)(ia - 1), *qb = a.node + 3 * (size_t)(ib - 1), *qc = a.node + 3 * (size_t)(ic - 1);
-            ox = ba * __ldg(qa) + bb * __ldg(qb) + bc * __ldg(qc);
-            oy = ba * __ldg(qa + 1) + bb * __ldg(qb + 1) + bc * __ldg(qc + 1);
-            oz = ba * __ldg(qa + 2) + bb * __ldg(qb + 2) + bc * __ldg(qc + 2);
-            Lp0 = sqrtf((ox - p.px) * (ox - p.px) + (oy - p.py) * (oy - p.py) + (oz - p.pz) * (oz - p.pz));
-            // outward face normals (BLB table: reflectray reads mesh->n for this tracer, :2272-2276): tab[36..47] = nx[4] ny[4] nz[4]
-            fnx = __ldg(rec->tab + 36 + fi);
-            fny = __ldg(rec->tab + 40 + fi);
-            fnz = __ldg(rec->tab + 44 + fi);
+            // exit point: p + t v on the plane of face fi, t = (d - N.p) / (N.v); outward normal for reflectray (:2272-2276)
+            fnx = sel4(r0, fi);
+            fny = sel4(r0 + 4, fi);
+            fnz = sel4(r1, fi);
+            const float S = p.vx * fnx + p.vy * fny + p.vz * fnz;
+            const float t = __fdividef(sel4(r1 + 4, fi) - (p.px * fnx + p.py * fny + p.pz * fnz), S);
+            Lp0 = (S > 0.f && t > 0.f) ? t : 0.f;
+            ox = p.px + Lp0 * p.vx;
+            oy = p.py + Lp0 * p.vy;
+            oz = p.pz + Lp0 * p.vz;
         }
     }
 
