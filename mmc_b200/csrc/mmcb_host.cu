@@ -23,6 +23,7 @@
 extern "C" int mmcb_k_upload_param(const mmcb_kparam* hp, const float* det4, int detnum, cudaStream_t st);
 extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int carveout,
                                      cudaStream_t st);
+extern "C" int mmcb_k_max_block(int method);
 extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int* blocks_per_sm);
 // mesh pre-processing on the device (mmcb_prep.cu)
 extern "C" int mmcb_k_facenb(const int* d_elem, int ne, int* d_facenb, cudaStream_t st);
@@ -1288,7 +1289,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     int smcount = 0, smemoptin = 0;       // two attributes instead of cudaGetDeviceProperties (several ms per call)
     CU(cudaDeviceGetAttribute(&smcount, cudaDevAttrMultiProcessorCount, device));
     CU(cudaDeviceGetAttribute(&smemoptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    s->block = (c.nblocksize > 0) ? c.nblocksize : 128;
+    s->block = (c.nblocksize > 0) ? std::min(c.nblocksize, mmcb_k_max_block(c.method)) : mmcb_k_max_block(c.method);
     s->block = std::max(32, (s->block / 32) * 32);
     s->smem_base = 2 * sizeof(float4) * m.med.size() + (s->isdet ? sizeof(float) * (size_t)devreclen * s->block : 0);
     s->hot_allowed = (c.hotcache >= 0 && srcnum == 1);

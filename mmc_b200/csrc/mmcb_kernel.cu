@@ -938,16 +938,20 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
 #define MMCB_PRAGMA_(x) _Pragma(#x)
 #define MMCB_UNROLL(n) MMCB_PRAGMA_(unroll n)
 #ifndef MMCB_MAXTHREADS
-#define MMCB_MAXTHREADS 128
+#define MMCB_MAXTHREADS 256      // BLB kernels: 4 CTAs x 256 threads per SM at 64 registers (measured against 8 x 128 and 16 x 64:
+                                 // +0.6 % sphshells grid, +1.2 % cube60, +3.4 % head-like with detector columns; profiles/r1j_tune_block.jsonl)
 #endif
 #ifndef MMCB_MINBLOCKS
-#define MMCB_MINBLOCKS 8
+#define MMCB_MINBLOCKS 4
+#endif
+#ifndef MMCB_MAXTHREADS_HP
+#define MMCB_MAXTHREADS_HP 128   // Havel / Plucker kernels (83-104 registers)
 #endif
 #ifndef MMCB_MINBLOCKS_HP
 #define MMCB_MINBLOCKS_HP 5      // measured: 4 -> 5 CTAs per SM +2 % (cube60) .. +8 % (sphshells), profiles/r1j_tune_hp_occupancy.jsonl
 #endif
 template <int METHOD, bool DET, bool GENERAL, bool RF = false>
-__global__ void __launch_bounds__(MMCB_MAXTHREADS, (METHOD <= 1) ? MMCB_MINBLOCKS_HP : MMCB_MINBLOCKS)
+__global__ void __launch_bounds__((METHOD <= 1) ? MMCB_MAXTHREADS_HP : MMCB_MAXTHREADS, (METHOD <= 1) ? MMCB_MINBLOCKS_HP : MMCB_MINBLOCKS)
 mmcb_photon_kernel(const mmcb_kargs a) {
     static_assert(!RF || (GENERAL && METHOD >= 3), "RF forward runs use the general branch-less Badouel kernels");
     constexpr bool GRID = (METHOD == 4);
@@ -1843,6 +1847,10 @@ extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, s
 
     k<<<grid, block, smem, st>>>(*a);
     return (int)cudaGetLastError();
+}
+
+extern "C" int mmcb_k_max_block(int method) {      // largest (and default) block size the kernel of this tracer is compiled for
+    return (method <= 1) ? MMCB_MAXTHREADS_HP : MMCB_MAXTHREADS;
 }
 
 extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int* blocks_per_sm) {

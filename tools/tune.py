@@ -11,9 +11,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "build", "variants")
 VARIANTS = {
-    "b128_hp4": ["-DMMCB_MINBLOCKS_HP=4"],
-    "b128_hp5": ["-DMMCB_MINBLOCKS_HP=5"],
-    "b128_hp6": ["-DMMCB_MINBLOCKS_HP=6"],
+    "b128_m8": ["-DMMCB_MAXTHREADS=128", "-DMMCB_MINBLOCKS=8"],
+    "b256_m4": ["-DMMCB_MAXTHREADS=256", "-DMMCB_MINBLOCKS=4", "-DMMCB_MINBLOCKS_HP=2"],
+    "b64_m16": ["-DMMCB_MAXTHREADS=64", "-DMMCB_MINBLOCKS=16", "-DMMCB_MINBLOCKS_HP=10"],
 }
 
 
