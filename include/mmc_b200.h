@@ -124,6 +124,10 @@ typedef struct mmcb_config {
                                     (x = disk radius), srcparam2 (w = enclosing element, filled by the library when 0) */
     const float* detdir;         /* detnum*4 detector normals (w = focal length): needed to turn detectors into adjoint sources */
     int   adjointmode;           /* mesh-mode J_mua: 0 full FEM form, 1 nodal approximation (cfg->adjointmode) */
+    /* per-node optical properties (cfg->nodemua / nodemusp with isnodalmua / isnodalmusp, src/mmc_core.cl:776-793): an element uses
+     * the mean of its four nodal values instead of its medium's mua (and mus); NULL = off; nodemusp needs nodemua */
+    const float* nodemua;        /* nn */
+    const float* nodemusp;       /* nn */
 } mmcb_config;
 
 typedef struct mmcb_gpuinfo {    /* src/mmc_utils.h:187-201 GPUInfo */

@@ -203,6 +203,8 @@ extern "C" void mmc_run_cu(mcconfig* cfg, tetmesh* mesh, raytracer* tracer) {
     c.srcdata = (const float*)cfg->srcdata;         // ExtraSrc = 4 x float4 (src/mmc_utils.h:147-152)
     c.detdir = (const float*)cfg->detdir;
     c.adjointmode = cfg->adjointmode;
+    c.nodemua = (cfg->isnodalmua && cfg->nodemua) ? cfg->nodemua : NULL;          // src/mmc_cu_host.cu:477-487
+    c.nodemusp = (c.nodemua && cfg->isnodalmusp && cfg->nodemusp) ? cfg->nodemusp : NULL;
 
     mmcb_sizes sz;
     B200_ASSERT(mmcb_query_sizes(&c, &m, &sz));

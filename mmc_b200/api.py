@@ -66,7 +66,7 @@ class Config(C.Structure):
                 ("savetraj", C.c_int), ("maxjumpdebug", C.c_uint),
                 ("nthread", C.c_int), ("nblocksize", C.c_int), ("schedule", C.c_int), ("respin", C.c_int), ("hotcache", C.c_int),
                 ("omega", C.c_float), ("srcid", C.c_int), ("extrasrclen", C.c_int), ("srcdata", C.c_void_p), ("detdir", C.c_void_p),
-                ("adjointmode", C.c_int)]
+                ("adjointmode", C.c_int), ("nodemua", C.c_void_p), ("nodemusp", C.c_void_p)]
 
 
 class GpuInfo(C.Structure):
@@ -217,7 +217,7 @@ DEFAULTS = dict(nphoton=0, seed=0x623F9A9E, srcpos=(0, 0, 0), srcdir=(0, 0, 1, 0
                 steps=(1.0, 1.0, 1.0), detpos=None, maxdetphoton=1000000, maxjumpdebug=10000000,
                 debuglevel="", nthread=0, nblocksize=0, schedule=0, respin=1, hotcache=0, gpuid=1,
                 replayseed=None, replayweight=None, replaytime=None,
-                omega=0.0, srcid=0, srcdata=None, detdir=None, adjointmode=0)
+                omega=0.0, srcid=0, srcdata=None, detdir=None, adjointmode=0, nodemua=None, nodemusp=None)
 
 
 class Problem:
@@ -297,6 +297,13 @@ class Problem:
             sd = np.ascontiguousarray(p["srcdata"], dtype=np.float32).reshape(-1, 16)
             self.keep.append(sd)
             c.extrasrclen, c.srcdata = len(sd), sd.ctypes.data
+        for k in ("nodemua", "nodemusp"):       # per-node optical properties (cfg.nodemua / cfg.nodemusp of pmmc)
+            if p[k] is not None:
+                a = np.ascontiguousarray(p[k], dtype=np.float32).ravel()
+                if len(a) != len(node):
+                    raise MMCError(-2, "%s needs one value per node" % k)
+                self.keep.append(a)
+                setattr(c, k, a.ctypes.data)
         if p["detdir"] is not None:
             dd = np.ascontiguousarray(p["detdir"], dtype=np.float32).reshape(-1, 4)
             if dd.shape[0] != c.detnum:

@@ -457,6 +457,14 @@ int validate(const mmcb_config* in, const mmcb_mesh* mesh, Cfg& o) {
         return fail(MMCB_ERR_INPUT, "RF forward runs do not support photon sharing (srcnum > 1)");
     }
 
+    if (c.nodemusp && !c.nodemua) {
+        return fail(MMCB_ERR_INPUT, "nodemusp needs nodemua (isnodalmusp is read only under isnodalmua, src/mmc_core.cl:785-793)");
+    }
+
+    if (c.nodemua && c.method != MMCB_RT_BLBADOUEL && c.method != MMCB_RT_BLBADOUEL_GRID) {
+        return fail(MMCB_ERR_INPUT, "per-node optical properties need the branch-less Badouel tracer (s or g), like the reference GPU path");
+    }
+
     const bool isadjoint = (c.outputtype >= MMCB_OT_ADJOINT);
 
     if (c.extrasrclen < 0 || (c.extrasrclen > 0 && !c.srcdata)) {
@@ -973,6 +981,7 @@ struct mmcb_session {
     void* d_field = NULL;
     void* d_field_im = NULL;       // RF: imaginary part
     float4* d_srcdata = NULL;      // multi-slot sources
+    float2* d_eprop = NULL;        // per-element means of the nodal optical properties
     double* d_dref = NULL;
     float* d_detected = NULL;
     unsigned int* d_detcount = NULL;
@@ -1023,6 +1032,7 @@ static int session_free(mmcb_session* s) {
 
     dev_free(s->d_field_im);
     dev_free(s->d_srcdata);
+    dev_free(s->d_eprop);
     dev_free(s->d_dref);
     dev_free(s->d_detected);
     dev_free(s->d_detcount);
@@ -1102,7 +1112,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     s->ishp = (c.method == MMCB_RT_PLUCKER || c.method == MMCB_RT_HAVEL);
     s->isdet = c.issavedet != 0;
     s->isgeneral = !(c.srctype == MMCB_SRC_PENCIL || c.srctype == MMCB_SRC_ISOTROPIC) || c.srcnum > 1 ||
-                   c.seed == MMCB_SEED_FROM_FILE || c.savetraj || c.issaveref || s->cfg.multisrc || s->cfg.isrf;
+                   c.seed == MMCB_SEED_FROM_FILE || c.savetraj || c.issaveref || s->cfg.multisrc || s->cfg.isrf || c.nodemua != NULL;
 
     // per-slot launch element (mesh_init_srcdata_eid, src/mmc_mesh.c:1114-1156): srcparam2.w of every slot that has none
     for (int slot = 0; slot < c.extrasrclen; slot++) {
@@ -1224,6 +1234,20 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
 
     if (c.extrasrclen > 0 && (rc = dev_alloc_copy((float**)&s->d_srcdata, s->cfg.srcdata.data(), s->cfg.srcdata.size()))) {
         return rc;
+    }
+
+    if (c.nodemua) {        // 0.25 * (sum of the four nodal values), in the reference's order of additions
+        std::vector<float2> ep(m.ne);
+
+        for (int i = 0; i < m.ne; i++) {
+            const int* ee = &m.elem[4 * (size_t)i];
+            ep[i].x = 0.25f * (c.nodemua[ee[0] - 1] + c.nodemua[ee[1] - 1] + c.nodemua[ee[2] - 1] + c.nodemua[ee[3] - 1]);     // used as given: the reference does not scale them by unitinmm
+            ep[i].y = c.nodemusp ? 0.25f * (c.nodemusp[ee[0] - 1] + c.nodemusp[ee[1] - 1] + c.nodemusp[ee[2] - 1] + c.nodemusp[ee[3] - 1]) : 0.f;
+        }
+
+        if ((rc = dev_alloc_copy(&s->d_eprop, ep.data(), ep.size()))) {
+            return rc;
+        }
     }
 
     if (c.issaveref) {
@@ -1383,6 +1407,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     k.extrasrclen = c.extrasrclen;
     k.slotstride = (unsigned int)(framelen * s->cfg.maxgate);
     k.omega = s->cfg.isrf ? c.omega : 0.f;
+    k.isnodalprop = c.nodemua ? (c.nodemusp ? 2 : 1) : 0;
     mmcb_kargs& a = s->ka;
     memset(&a, 0, sizeof(a));
     a.tet = s->d_tet;
@@ -1402,6 +1427,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     a.field = s->d_field;
     a.field_im = s->d_field_im;
     a.srcdata = s->d_srcdata;
+    a.eprop = s->d_eprop;
     a.dref = s->d_dref;
     a.detected = s->d_detected;
     a.detcount = s->d_detcount;

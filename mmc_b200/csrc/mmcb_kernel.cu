@@ -1168,7 +1168,19 @@ mmcb_photon_kernel(const mmcb_kargs a) {
 
         if (found) {
             prop = smed[2 * type];                          // mua mus g n
-            const float4 pd = smed[2 * type + 1];           // 1/mus (0: none), n/c0, 1/mua (0: mua < EPS), c0/n
+            float4 pd = smed[2 * type + 1];                 // 1/mus (0: none), n/c0, 1/mua (0: mua < EPS), c0/n
+
+            if (GENERAL && gp.isnodalprop) {                // per-node optical properties: element means (:776-793)
+                const float2 ep = __ldg(a.eprop + (p.eid - 1));
+                prop.x = ep.x;
+                pd.z = (ep.x < EPS) ? 0.f : __frcp_rn(ep.x);
+
+                if (gp.isnodalprop > 1) {
+                    prop.y = ep.y;
+                    pd.x = (ep.y <= EPS) ? 0.f : __frcp_rn(ep.y);
+                }
+            }
+
             Lmove = (pd.x == 0.f) ? R_MIN_MUS : p.slen * pd.x;
             isend = (Lmin > Lmove);
             Lmove = isend ? Lmove : Lmin;

@@ -97,6 +97,7 @@ struct mmcb_kparam {
     int   extrasrclen;           // slots in kargs.srcdata
     unsigned int slotstride;     // framelen * maxgate: offset between the slots' blocks of the accumulator volume
     float omega;                 // modulation angular frequency (rad/s); > 0 only in the RF kernel variants
+    int   isnodalprop;           // 0 off; 1 kargs.eprop[e].x overrides mua; 2 .y overrides mus as well (src/mmc_core.cl:776-793)
 };
 
 struct mmcb_kargs {
@@ -116,6 +117,7 @@ struct mmcb_kargs {
     const float* replaytime;
     void*   field;               // accumulator volume
     void*   field_im;            // RF: imaginary part, same layout
+    const float2* eprop;         // per-element {mua, mus}: means of the four nodal values (per-node optical properties)
     const float4* srcdata;       // multi-slot sources: 4 float4 per slot {srcpos(w: weight), srcdir(w: focal length), srcparam1, srcparam2(w: e0)}
     double* dref;
     float*  detected; unsigned int* detcount; unsigned long long* detseed;

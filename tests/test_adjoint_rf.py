@@ -207,3 +207,37 @@ def test_mesh_adjoint_jacobians_match_the_numpy_oracle(omega):
         assert ok.sum() > 20
         np.testing.assert_allclose(ratio[0][ok], ratio[1][ok], rtol=1e-4)
         assert (ratio[0][ok] > 0.5).all() and (ratio[0][ok] < 2.0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["elem", "grid"])
+def test_per_node_optical_properties(method):
+    """cfg.nodemua / cfg.nodemusp (src/mmc_core.cl:776-793): an element takes the mean of its four nodal values.  Nodal arrays that
+    repeat the media table must reproduce the ordinary run exactly (same photons: static schedule); raising the nodal absorption
+    raises the absorbed fraction; mus from nodemusp changes the step count."""
+    c = _cfg(method=method, steps=(1.0, 1.0, 1.0), nphoton=100000, schedule=1, hotcache=-1, isnormalized=0, tstep=5e-10)
+    node, elem, et = np.asarray(c["node"]), np.asarray(c["elem"]), np.asarray(c["elemprop"])
+    prop = np.asarray(c["prop"], np.float32)
+    base = mmc.run(c)
+    # uniform medium 1 everywhere (labels kept): nodal values = medium 1
+    c1 = dict(c, prop=np.vstack([prop[0], prop[1], prop[1]]))
+    ref1 = mmc.run(c1)
+    nod = mmc.run(dict(c1, nodemua=np.full(len(node), prop[1, 0], np.float32), nodemusp=np.full(len(node), prop[1, 1], np.float32)))
+    assert nod["raytet"] == ref1["raytet"]
+    np.testing.assert_allclose(nod["energyesc"], ref1["energyesc"], rtol=1e-6)
+    np.testing.assert_allclose(nod["raw"].sum(), ref1["raw"].sum(), rtol=1e-6)
+    # mua only: trajectories are unchanged (same scattering), absorption follows the nodal field
+    hi = mmc.run(dict(c1, nodemua=np.full(len(node), 4 * prop[1, 0], np.float32)))
+    assert hi["raytet"] <= ref1["raytet"] * 1.0001            # photons are weighted, not killed, but time gates are the same
+    fa = lambda r: r["energyabs"][0] / r["energytot"][0]
+    assert fa(hi) > 1.5 * fa(ref1)
+    # a nodal field that varies in space: absorbed fraction lies between the two uniform cases
+    z = node[:, 2]
+    mid = mmc.run(dict(c1, nodemua=np.where(z > 10, 4 * prop[1, 0], prop[1, 0]).astype(np.float32)))
+    assert fa(ref1) < fa(mid) < fa(hi)
+    # musp: doubling the scattering coefficient raises the number of ray-tet steps per photon
+    more = mmc.run(dict(c1, nodemua=np.full(len(node), prop[1, 0], np.float32), nodemusp=np.full(len(node), 2 * prop[1, 1], np.float32)))
+    assert more["raytet"] > 1.2 * ref1["raytet"]
+    assert base["raytet"] > 0
+    with pytest.raises(mmc.MMCError, match="branch-less Badouel"):
+        mmc.run(dict(c1, method="havel", nodemua=np.full(len(node), 0.01, np.float32)))
