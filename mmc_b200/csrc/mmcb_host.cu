@@ -1681,7 +1681,13 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
     n0 = std::min(n0, nphoton / 2);
     CU(cudaEventRecord(s->ev0, st));
 
-    if (pilot && s->cfg.maxgate > 1 && s->cfg.nslots == 1 && !getenv("MMCB_NO_SCOUT")) {
+    const bool scout = pilot && s->cfg.maxgate > 1 && s->cfg.nslots == 1 && !getenv("MMCB_NO_SCOUT");
+
+    if (scout) {            // a few ten thousand photons rank the lines near the source well enough (the selection works on ratios)
+        n0 = std::min<uint64_t>(std::max<uint64_t>(nphoton / 256, 16384), 65536);
+    }
+
+    if (scout) {
         const size_t flen = (size_t)s->kp.framelen * c.srcnum, accsize = s->acc_double ? 8 : 4;
         char* scr = NULL;           // [volume of gate 0][energy tot/esc][raytet][detcount, trajcount]
         const size_t tail = sizeof(double) * (2 * MMCB_MAX_SRCNUM + 1) + 2 * sizeof(unsigned int), voff = (flen * accsize + 15) / 16 * 16;
