@@ -165,7 +165,8 @@ typedef struct mmcb_output {
 } mmcb_output;
 
 typedef struct mmcb_sizes {
-    int maxgate, datalen, reclen, nf, srcnum;
+    int maxgate, datalen, reclen, nf, srcnum;   /* nf (exterior faces, dref length nf*maxgate): from mmcb_query_sizes only when
+                                                   cfg.issaveref is set (it costs the face-neighbour table); always from a session */
     int dim[3];                  /* dual-grid dimensions (cfg->dim) */
     size_t fieldlen;             /* datalen*maxgate*srcnum*nslots */
     int nslots;                  /* field blocks: extrasrclen in multi-slot mode (srcid < 0), else 1; block stride datalen*maxgate */
@@ -217,6 +218,9 @@ int  mmcb_reset(mmcb_session* s);            /* zero all accumulators */
  * floats -- and the prepared face-neighbour table (ne*4, exterior faces numbered -1..-nf like tracer_prep); any pointer may be NULL */
 int  mmcb_get_tables(mmcb_session* s, void* tetrec_out, float* cent_out, int* facenb_out);
 void mmcb_destroy(mmcb_session* s);
+/* what mmcb_run_simulation does, on an existing session: all `respin` launches of cfg.nphoton photons, then mmcb_fetch.  With mmcb_create + mmcb_get_sizes in front
+ * the caller sizes its output arrays from the session and the mesh is prepared once (mmcb_query_sizes prepares it a second time) */
+int mmcb_run_session(mmcb_session* s, mmcb_output* out);
 
 /* ---- host-side mesh helpers (what mmc_prep/tracer_prep compute; exposed for callers and tests) ------- */
 int mmcb_mesh_volumes(int nn, const float* node, int ne, int* elem_inout, const int* type, float* evol, float* nvol); /* mesh_getvolume src/mmc_mesh.c:910 */

@@ -206,8 +206,16 @@ extern "C" void mmc_run_cu(mcconfig* cfg, tetmesh* mesh, raytracer* tracer) {
     c.nodemua = (cfg->isnodalmua && cfg->nodemua) ? cfg->nodemua : NULL;          // src/mmc_cu_host.cu:477-487
     c.nodemusp = (c.nodemua && cfg->isnodalmusp && cfg->nodemusp) ? cfg->nodemusp : NULL;
 
+    // one session: the mesh is prepared once (face neighbours and tracer tables on the device), the output arrays are sized from it
+    int device = (cfg->deviceid[0] > 0 ? cfg->deviceid[0] : 1) - 1;    // the first enabled GPU; more GPUs: mmc_b200/multigpu.py
+    mmcb_session* sess = mmcb_create(&c, &m, device);
+
+    if (!sess) {
+        B200_ASSERT(-1);
+    }
+
     mmcb_sizes sz;
-    B200_ASSERT(mmcb_query_sizes(&c, &m, &sz));
+    B200_ASSERT(mmcb_get_sizes(sess, &sz));
 
     // ---- outputs (ownership as in src/mmc_cu_host.cu:339-367: exportfield defaults to mesh->weight; detected rows and
     //      seeds are malloc'ed here and freed by the caller)
@@ -263,8 +271,8 @@ extern "C" void mmc_run_cu(mcconfig* cfg, tetmesh* mesh, raytracer* tracer) {
     MMC_FPRINTF(cfg->flog, "lauching mmc_main_loop for time window [%.1fns %.1fns] ...\n", cfg->tstart * 1e9, cfg->tend * 1e9);
     mcx_fflush(cfg->flog);
     unsigned int tic = StartTimer();
-    int device = (cfg->deviceid[0] > 0 ? cfg->deviceid[0] : 1) - 1;    // the first enabled GPU; more GPUs: mmc_b200/multigpu.py
-    B200_ASSERT(mmcb_run_simulation(&c, &m, device, &out));
+    B200_ASSERT(mmcb_run_session(sess, &out));
+    mmcb_destroy(sess);
     unsigned int toc = GetTimeMillis() - tic;
     MMC_FPRINTF(cfg->flog, "kernel complete:  \t%d ms\nretrieving flux ... \t", (int)(out.kernel_ms + 0.5f));
     MMC_FPRINTF(cfg->flog, "transfer complete:        %d ms\n", toc);

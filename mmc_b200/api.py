@@ -100,7 +100,7 @@ class DevPtrs(C.Structure):
 
 EXPORTS = ["mmcb_version", "mmcb_last_error", "mmcb_list_gpu", "mmcb_query_sizes", "mmcb_run_simulation",
            "mmcb_create", "mmcb_set_field_buffer", "mmcb_launch", "mmcb_sync", "mmcb_last_kernel_ms",
-           "mmcb_get_devptrs", "mmcb_get_sizes", "mmcb_fetch", "mmcb_reset", "mmcb_destroy", "mmcb_get_tables",
+           "mmcb_get_devptrs", "mmcb_get_sizes", "mmcb_fetch", "mmcb_reset", "mmcb_destroy", "mmcb_get_tables", "mmcb_run_session",
            "mmcb_mesh_volumes", "mmcb_mesh_facenb", "mmcb_mesh_initelem", "mmcb_host_seeds", "mmcb_rng_selftest"]
 
 _lib = None
@@ -129,6 +129,7 @@ def lib():
         L.mmcb_get_sizes.argtypes = [C.c_void_p, C.POINTER(Sizes)]
         L.mmcb_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Output)]
         L.mmcb_reset.argtypes = [C.c_void_p]
+        L.mmcb_run_session.argtypes = [C.c_void_p, C.POINTER(Output)]
         L.mmcb_get_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mmcb_list_gpu.argtypes = [C.POINTER(GpuInfo), C.c_int]
         L.mmcb_mesh_volumes.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -543,7 +543,9 @@ int validate(const mmcb_config* in, const mmcb_mesh* mesh, Cfg& o) {
 
 // gpu_stream: when not NULL (session path, device selected) the face-neighbour table is built on the device (mmcb_prep.cu);
 // the host sort remains for mmcb_query_sizes / mmcb_mesh_facenb, which must work without a GPU
-int prepare_mesh(const mmcb_mesh* in, Cfg& cfg, PrepMesh& m, cudaStream_t gpu_stream = NULL, bool use_gpu = false) {
+// sizes_only: mmcb_query_sizes needs the counts, not the tables -- the face-neighbour sort (the one expensive host step) runs only when
+// nf (the exterior-face count behind the diffuse-reflectance length) is asked for
+int prepare_mesh(const mmcb_mesh* in, Cfg& cfg, PrepMesh& m, cudaStream_t gpu_stream = NULL, bool use_gpu = false, bool sizes_only = false) {
     mmcb_config& c = cfg.c;
 
     if (in->nn <= 0 || in->ne <= 0 || !in->node || !in->elem || !in->type || !in->med || in->prop < 1) {
@@ -632,7 +634,11 @@ int prepare_mesh(const mmcb_mesh* in, Cfg& cfg, PrepMesh& m, cudaStream_t gpu_st
 
     m.facenb.resize(4 * (size_t)m.ne);
 
-    if (in->facenb) {
+    const bool skip_facenb = sizes_only && !c.issaveref;
+
+    if (skip_facenb) {
+        std::fill(m.facenb.begin(), m.facenb.end(), 1);        // placeholder: no exterior faces are counted, nf stays 0
+    } else if (in->facenb) {
         for (size_t i = 0; i < m.facenb.size(); i++) {
             m.facenb[i] = in->facenb[i] > 0 ? in->facenb[i] : 0;
         }
@@ -1578,7 +1584,7 @@ int mmcb_query_sizes(const mmcb_config* cfg, const mmcb_mesh* mesh, mmcb_sizes* 
         return rc;
     }
 
-    if ((rc = prepare_mesh(mesh, c, m))) {
+    if ((rc = prepare_mesh(mesh, c, m, NULL, false, true))) {
         return rc;
     }
 
@@ -2377,19 +2383,12 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
     return 0;
 }
 
-int mmcb_run_simulation(const mmcb_config* cfg, const mmcb_mesh* mesh, int device, mmcb_output* out) {
-    if (!out) {
-        return fail(MMCB_ERR_INPUT, "null output");
+int mmcb_run_session(mmcb_session* s, mmcb_output* out) {
+    if (!s || !out) {
+        return fail(MMCB_ERR_INPUT, "null argument");
     }
 
     Trace tr;
-    mmcb_session* s = mmcb_create(cfg, mesh, device);
-
-    if (!s) {
-        return g_code ? g_code : MMCB_ERR_CUDA;
-    }
-
-    tr.mark("run: create");
     int rc = 0;
     float ms = 0.f;
     const int respin = s->cfg.c.respin;
@@ -2414,6 +2413,23 @@ int mmcb_run_simulation(const mmcb_config* cfg, const mmcb_mesh* mesh, int devic
     }
 
     tr.mark("run: fetch");
+    return rc;
+}
+
+int mmcb_run_simulation(const mmcb_config* cfg, const mmcb_mesh* mesh, int device, mmcb_output* out) {
+    if (!out) {
+        return fail(MMCB_ERR_INPUT, "null output");
+    }
+
+    Trace tr;
+    mmcb_session* s = mmcb_create(cfg, mesh, device);
+
+    if (!s) {
+        return g_code ? g_code : MMCB_ERR_CUDA;
+    }
+
+    tr.mark("run: create");
+    int rc = mmcb_run_session(s, out);
     std::string keep = g_err;
     mmcb_destroy(s);
     g_err = keep;
