@@ -29,14 +29,14 @@ extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, i
 extern "C" int mmcb_k_facenb(const int* d_elem, int ne, int* d_facenb, cudaStream_t st);
 extern "C" int mmcb_k_build_records(const float* d_node, const int* d_elem, const int* d_facenb, const int* d_type, const float* d_med_n, int ne,
                                     float nout, int isreflect, mmcb_tetrec* d_rec, float4* d_cent, cudaStream_t st);
-// mesh_normalize on the device (mmcb_adjoint.cu)
+// mesh_normalize on the device (mmcb_post.cu)
 extern "C" int mmcb_k_norm_sum(const double* W, size_t nentry, int srcnum, double* dep, cudaStream_t st);
 extern "C" int mmcb_k_norm_nvol(double* W, size_t n, int nn, int srcnum, const float* nvol, cudaStream_t st);
 extern "C" int mmcb_k_norm_elemdep(const double* W, const int* elem, const float* evol, const float* emua, int ne, int nn, int maxgate, int srcnum,
                                    double* dep, cudaStream_t st);
 extern "C" int mmcb_k_norm_scale(const double* in, double* out, size_t n, int datalen, int srcnum, const float* evol, const float* emua,
                                  const double* fac16, cudaStream_t st);
-// adjoint-Jacobian post-kernels (mmcb_adjoint.cu)
+// adjoint-Jacobian post-kernels (mmcb_post.cu)
 extern "C" int mmcb_k_adj_cw(const float* field, float* cw, size_t N, int maxgate, int nslots, cudaStream_t st);
 extern "C" int mmcb_k_adj_mua(const float* cw_re, const float* cw_im, float* out, size_t N, int Ns, int Nd, float scale, cudaStream_t st);
 extern "C" int mmcb_k_adj_dcoeff(const float* cw_re, const float* cw_im, float* out, size_t N, int Ns, int Nd, unsigned int Nx, unsigned int Ny,

@@ -1,4 +1,4 @@
-// Adjoint-Jacobian post-kernels of mmc_b200 (sm_100a): what the reference runs after a multi-slot (sources + detectors-as-sources)
+// Post-processing kernels of mmc_b200 (sm_100a): mesh_normalize on the device (end of file) and the adjoint-Jacobian kernels, i.e. what the reference runs after a multi-slot (sources + detectors-as-sources)
 // forward simulation to turn the slots' fluence volumes into Jacobians (src/mmc_core.cl:2218-2649, driven by
 // src/mmc_cu_host.cu:1063-1395).  All of them are streaming, HBM/L2-bound kernels.
 //

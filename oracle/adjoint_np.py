@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE (oracle): numpy restatement of the reference's adjoint-Jacobian post-processing -- the four kernels of
 src/mmc_core.cl:2218-2649 as driven by src/mmc_cu_host.cu:1063-1395 -- used by tests/ to check the CUDA post-kernels of
-mmc_b200/csrc/mmcb_adjoint.cu.  Only tests/ may import this; nothing under mmc_b200/ does.
+mmc_b200/csrc/mmcb_post.cu.  Only tests/ may import this; nothing under mmc_b200/ does.
 
 Parity status: the reference implements these kernels on the GPU only (the CPU program has no adjoint path) and ships no
 golden vectors for them, so this restatement is pinned by construction (formula by formula, float32 like the kernels), not by a

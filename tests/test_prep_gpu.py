@@ -68,7 +68,7 @@ def test_device_prep_gives_the_same_simulation():
 @pytest.mark.parametrize("name", ["blb_elem_reflect", "blb_nodal_reflect", "grid_1mm", "havel_nodal", "plucker_elem", "blb_energy", "blb_fluence",
                                   "pattern_share2", "blb_dref"])
 def test_device_normalisation_equals_host_normalisation(name):
-    """mesh_normalize (src/mmc_mesh.c:2154-2279) on the device (mmcb_adjoint.cu: mmcb_norm_*) against the host restatement of the same
+    """mesh_normalize (src/mmc_mesh.c:2154-2279) on the device (mmcb_post.cu: mmcb_norm_*) against the host restatement of the same
     function kept in mmcb_host.cu, on identical raw volumes (static schedule, same seeds).  The reductions run in a different order:
     rtol 1e-10."""
     import test_gpu_parity as tp
