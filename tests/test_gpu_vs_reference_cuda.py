@@ -69,3 +69,40 @@ def test_sphshells_grid_fluence_vs_reference_cuda_1e8():
     print("sphshells grid: %d lit voxels, median %.4f, p99 %.4f, worst %.4f" % (n, med_, p99, worst))
     assert n > 2000
     assert med_ < 0.005 and p99 < 0.015 and worst < 0.02, (med_, p99, worst)    # measured: 0.0015 / 0.0070 / 0.0120
+
+
+@needs_refcuda
+def test_rf_real_part_vs_reference_cuda_1e7():
+    """RF forward run (omega = 2 pi 200 MHz), dual-grid deposit: the reference CLI keeps only the real part of the complex fluence
+    (cfg->exportadjoint is returned by mmclab/pmmc, never written by mesh_saveweight), so that is what its CUDA kernel can pin:
+    complex Beer-Lambert per segment (src/mmc_core.cl:1043-1078), |w| energy bookkeeping (:2150-2152).  The imaginary part is
+    checked against the Fourier transform of the time-resolved run in tests/test_adjoint_rf.py."""
+    node, elem, et, med = cases.two_media_cube()
+    omega = 2 * np.pi * 2e8
+    N = 10000000
+    kw = dict(nphoton=N, seed=1648335518, srcpos=(10.1, 10.2, 0.0), srcdir=(0, 0, 1), tstart=0.0, tend=5e-9, tstep=5e-10,
+              isreflect=1, method=cases.GRID, basisorder=0, steps=1.0, isnormalized=0,
+              e0=int(mmc.mesh_initelem(node, elem, (10.1, 10.2, 0.0))[0]))      # the JSON overlay insists on an explicit InitElem
+    # check=False: the reference saves its volume, prints its summary and then dies in its own clean-up ("free(): invalid size") in RF runs
+    r = orc.run_ref(node, elem, et, med, cuda=True, timeout=600, check=False, extra_args=["-j", '{"Forward":{"T0":0,"T1":5e-9,"Dt":5e-10,"N0":1,"Omega":%.9g}}' % omega], **kw)      # the overlay resets the gates it does not name
+    g = mmc.run(dict(node=node, elem=elem, elemprop=et, prop=np.vstack([[0, 0, 1, 1], med]), method="grid", steps=(1.0, 1.0, 1.0),
+                     omega=omega, **{k: v for k, v in kw.items() if k not in ("method", "steps")}))
+    fg = g["energyabs"][0] / g["energytot"][0]
+    if "absorbed_frac" in r:
+        assert abs(fg - r["absorbed_frac"]) < 2e-3 * fg, (fg, r["absorbed_frac"])     # |w| bookkeeping: absorbed fraction as in the CW run
+    ref = r["field_flat"].reshape(10, -1).sum(axis=0)
+    ours = g["raw"][..., 0].sum(axis=0)
+    assert ref.shape == ours.shape
+    lit = np.abs(ref) > 1e-2 * np.abs(ref).max()
+    rel = np.abs(ours[lit] - ref[lit]) / np.abs(ref[lit])
+    print("RF real part: %d lit voxels, median %.4f, p99 %.4f" % (lit.sum(), np.median(rel), np.percentile(rel, 99)))
+    assert lit.sum() > 300
+    assert np.median(rel) < 0.01 and np.percentile(rel, 99) < 0.06, (np.median(rel), np.percentile(rel, 99))
+    assert abs(ours[lit].sum() / ref[lit].sum() - 1) < 2e-3
+    # the phase rotation is visible in the real part: it differs from the CW fluence of the same problem
+    cw = mmc.run(dict(node=node, elem=elem, elemprop=et, prop=np.vstack([[0, 0, 1, 1], med]), method="grid", steps=(1.0, 1.0, 1.0),
+                      **{k: v for k, v in dict(kw, nphoton=1000000).items() if k not in ("method", "steps")}))
+    cwv = cw["raw"][..., 0].sum(axis=0) * (N / 1e6)
+    dcw = np.median(np.abs(cwv[lit] - ref[lit]) / np.abs(ref[lit]))
+    print("CW vs RF real part: median %.4f" % dcw)
+    assert dcw > 0.01 and dcw > 4 * np.median(rel)
