@@ -326,7 +326,7 @@ def main():
                          "gsteps_per_s": steps_per_launch / (kernel_ms * 1e-3) / 1e9,
                          "note": "algorithmic bytes = %d B per ray-tet step x %.3g steps per launch.  Mesh tables and volume are L2-resident (DRAM traffic "
                                  "per launch is the `traffic` field), so the kernel is not HBM-bound: ncu at 1e7 photons shows 84%% issue slots busy, IPC 3.33 (sphshells grid; 72%% cube60 elem): "
-                                 "instruction-issue bound (profiles/r1j_ncu_*); measured L2 ceilings on this box: 130-150 G record gathers/s, 196 G red/s, 0.7 G red/s on one 128 B line "
+                                 "instruction-issue bound (profiles/r1k_ncu_*); measured L2 ceilings on this box: 130-150 G record gathers/s, 196 G red/s, 0.7 G red/s on one 128 B line "
                                  "(profiles/r1_microbench_l2gather_atomics.jsonl)" % (bps, steps_per_launch)}}
     if e2e is not None:
         line["e2e"] = e2e

@@ -329,28 +329,10 @@ class Problem:
         return s
 
 
-def _host_buffer(n, dtype):
-    """Uninitialised host array for a result volume.  Large volumes come from an anonymous mapping advised to use transparent huge
-    pages: the device-to-host copy of a fresh 50 MB array otherwise spends most of its time in 4 KB first-touch page faults."""
-    nbytes = int(n) * np.dtype(dtype).itemsize
-    if nbytes >= (4 << 20) and not os.environ.get("MMCB_NO_THP"):
-        try:
-            import mmap
-            mm = mmap.mmap(-1, nbytes + (2 << 20), flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
-            if hasattr(mm, "madvise") and hasattr(mmap, "MADV_HUGEPAGE"):
-                mm.madvise(mmap.MADV_HUGEPAGE)
-            base = np.frombuffer(mm, dtype=np.uint8)
-            off = (-base.ctypes.data) % (2 << 20)               # start on a 2 MB boundary
-            return base[off:off + nbytes].view(dtype)
-        except (OSError, ValueError, ImportError):
-            pass
-    return np.empty(int(n), dtype=dtype)
-
-
 class _OutBuffers:
     def __init__(self, prob, sz):
         c = prob.cfg
-        self.field = _host_buffer(sz.fieldlen, np.float64)        # overwrite=1: filled by the library
+        self.field = np.empty(sz.fieldlen, dtype=np.float64)      # overwrite=1: filled by the library
         self.dref = np.zeros(max(1, sz.nf * sz.maxgate), dtype=np.float64) if c.issaveref else None
         nd = int(c.maxdetphoton) if c.issavedet else 0
         self.detected = np.zeros((max(nd, 1), sz.reclen), dtype=np.float32)
