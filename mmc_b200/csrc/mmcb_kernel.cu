@@ -1013,6 +1013,12 @@ mmcb_photon_kernel(const mmcb_kargs a) {
     const int reclen = gp.reclen;
     const int M = gp.maxmedia;
 #define PPATH(k) ppath[(k) * blockDim.x + threadIdx.x]
+    // detected-photon bookkeeping of the medium the photon is in: path length, scattering count and momentum transfer are summed in
+    // registers and written to the shared-memory columns when the medium changes or the photon ends (the reference updates
+    // ppath[] in memory every step, src/mmc_core.cl:1943-1945,2128-2134)
+    int acct = 0;
+    float accL = 0.f, accN = 0.f, accM = 0.f;
+#define PPATH_FLUSH() do { if (acct > 0 && acct <= M) { PPATH(M + acct - 1) += accL; PPATH(acct - 1) += accN; if (gp.ismomentum) { PPATH(2 * M + acct - 1) += accM; } } accL = accN = accM = 0.f; } while (0)
 
     while (true) {
         // ------------------------------------------------------------------ photon supply
@@ -1367,8 +1373,13 @@ mmcb_photon_kernel(const mmcb_kargs a) {
             // trapped between degenerate/inverted tetrahedra (the reference CPU path spins forever there) and is dropped
             p.fixcount = (Lmove > 0.f) ? 0 : (p.fixcount + 0x100);
 
-            if (DET && Lmove > 0.f && type > 0 && type <= M) {           // :1943-1945
-                PPATH(M + type - 1) += Lmove;
+            if (DET) {                                      // :1943-1945
+                if (type != acct) {
+                    PPATH_FLUSH();
+                    acct = type;
+                }
+
+                accL += Lmove;
             }
 
             if (timeup || p.fixcount >= (MMCB_MAX_STALL << 8)) {
@@ -1432,12 +1443,9 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                         savedebug(p, a);
                     }
 
-                    if (DET && type > 0 && type <= M) {
-                        if (gp.ismomentum) {
-                            PPATH(2 * M + type - 1) += mom;
-                        }
-
-                        PPATH(type - 1) += 1.f;
+                    if (DET) {              // type == acct here: the step above set it
+                        accM += mom;
+                        accN += 1.f;
                     }
                 }
             }
@@ -1455,6 +1463,11 @@ mmcb_photon_kernel(const mmcb_kargs a) {
 
         // ------------------------------------------------------------------ photon end: tallies + detection
         if (terminate) {
+            if (DET) {
+                PPATH_FLUSH();
+                acct = 0;
+            }
+
             if (detect) {
                 if (GENERAL && gp.issaveref && exiteid < 0 && a.dref) {     // src/mmc_raytrace.c:2000-2003
                     int g = min((int)((p.t - gp.tstart) * gp.Rtstep), gp.maxgate - 1);
@@ -1549,6 +1562,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
         }
     }
 
+#undef PPATH_FLUSH
 #undef PPATH
     // the stream state goes back in the seed-word packing: the next launch of the session may continue the streams
     *(uint4*)(a.seeds + 4 * (size_t)tid) = make_uint4((unsigned int)(rng.t0 >> 32), (unsigned int)rng.t0, (unsigned int)(rng.t1 >> 32), (unsigned int)rng.t1);
