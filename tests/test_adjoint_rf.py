@@ -241,3 +241,26 @@ def test_per_node_optical_properties(method):
     assert base["raytet"] > 0
     with pytest.raises(mmc.MMCError, match="branch-less Badouel"):
         mmc.run(dict(c1, method="havel", nodemua=np.full(len(node), 0.01, np.float32)))
+
+
+def test_fd_gradient_oracle_matches_numpy_second_order():
+    """oracle/adjoint_np.fd_grad restates mmc_fd_grad (src/mmc_core.cl:2247-2285): central differences inside, second-order one-sided
+    differences at the ends -- the scheme of numpy.gradient(edge_order=2) for unit spacing; exact on quadratics."""
+    rs = np.random.RandomState(5)
+    vol = rs.rand(7, 6, 5).astype(np.float32)
+    for axis in range(3):
+        np.testing.assert_allclose(adjoint_np.fd_grad(vol, axis), np.gradient(vol.astype(np.float64), axis=axis, edge_order=2), rtol=2e-5, atol=2e-6)
+    z, y, x = np.meshgrid(np.arange(7.0), np.arange(6.0), np.arange(5.0), indexing="ij")
+    q = (0.5 * x * x - 2 * y * y + 0.25 * z * z + x * y).astype(np.float32)
+    np.testing.assert_allclose(adjoint_np.fd_grad(q, 2), x + y, atol=1e-4)          # d/dx, x fastest
+    np.testing.assert_allclose(adjoint_np.fd_grad(q, 1), -4 * y + x, atol=1e-4)
+    np.testing.assert_allclose(adjoint_np.fd_grad(q, 0), 0.5 * z, atol=1e-4)
+    two = rs.rand(2, 3, 4).astype(np.float32)                                        # N == 2: plain difference on both ends
+    np.testing.assert_allclose(adjoint_np.fd_grad(two, 0), np.stack([two[1] - two[0]] * 2))
+    # Jacobian products on a tiny volume: J_mua = -phi_s phi_d, J_D = -grad phi_s . grad phi_d (scale -1)
+    cw = rs.rand(3, 7 * 6 * 5).astype(np.float32)
+    jm, _ = adjoint_np.jmua_grid(cw, None, 1, 2, -1.0)
+    np.testing.assert_allclose(jm[1], -cw[0] * cw[2], rtol=1e-6)
+    jd, _ = adjoint_np.jd_grid(cw, None, 1, 2, (5, 6, 7), -1.0)
+    g = lambda k: np.stack(np.gradient(cw[k].astype(np.float64).reshape(7, 6, 5), edge_order=2))
+    np.testing.assert_allclose(jd[0], -(g(0) * g(1)).sum(axis=0).ravel(), rtol=2e-4, atol=2e-5)
