@@ -89,3 +89,39 @@ def test_config_validation_mirrors_reference_messages():
         api.Problem(bad).sizes()
     g = api.Problem(dict(cfg, method="grid", steps=(0.5, 0.5, 0.5))).sizes()
     assert tuple(g.dim) == (41, 41, 41) and g.datalen == 41 ** 3        # mesh_createdualmesh, src/mmc_mesh.c:374-380
+
+
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
+    """include/mmc_b200.h must be consumable from C (the reference host is C): compile a C99 program against it with gcc -pedantic,
+    link it to the library, call the entry points that need no GPU, and compare sizeof() of every struct with the ctypes mirrors of
+    mmc_b200/api.py (a field added on one side only would shift everything behind it)."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "mmc_b200.h"
+int main(void) {
+    mmcb_config c; mmcb_mesh m; mmcb_output o; mmcb_sizes s; mmcb_devptrs d; mmcb_gpuinfo g;
+    uint32_t seeds[8];
+    (void)c; (void)m; (void)o; (void)s; (void)d; (void)g;
+    mmcb_host_seeds(1648335518, 0, 8, seeds);
+    printf("%d %zu %zu %zu %zu %zu %zu %u %d\n", mmcb_version(), sizeof(mmcb_config), sizeof(mmcb_mesh), sizeof(mmcb_output),
+           sizeof(mmcb_sizes), sizeof(mmcb_devptrs), sizeof(mmcb_gpuinfo), seeds[0], mmcb_query_sizes(NULL, NULL, &s));
+    printf("%s\n", mmcb_last_error());
+    return 0;
+}
+''')
+    exe = tmp_path / "t"
+    libdir = os.path.dirname(api.LIBPATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-o", str(exe), "-L", libdir, "-lmmc_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([str(exe)]).decode().splitlines()
+    v = out[0].split()
+    assert int(v[0]) == 0x00010000
+    sizes = [int(x) for x in v[1:7]]
+    assert sizes == [ctypes.sizeof(t) for t in (api.Config, api.Mesh, api.Output, api.Sizes, api.DevPtrs, api.GpuInfo)]
+    assert int(v[7]) == int(orc.host_seeds(1648335518, 1)[0])
+    assert int(v[8]) < 0 and "null" in out[1]                          # error convention: negative id + message
