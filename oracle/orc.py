@@ -16,6 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "liboracle.so")
 REF_BIN = os.path.join(HERE, "_ref", "mmc_ref")
 REF_CUDA_BIN = os.path.join(HERE, "_ref", "mmc_refcuda")
+REF_CUDA_MS_BIN = os.path.join(HERE, "_ref", "mmc_refcuda_ms")    # reference CUDA objects behind ref_multislot_main.c
 
 PLUCKER, HAVEL, BADOUEL, BLBADOUEL, GRID = 0, 1, 2, 3, 4
 FLUX, FLUENCE, ENERGY, JACOBIAN, WL, WP = 0, 1, 2, 3, 4, 5
@@ -227,8 +228,8 @@ def run(node, elem, etype, med, facenb=None, evol=None, **kw):
 # ---------------------------------------------------------------------------------------------------
 # the unmodified reference binary
 # ---------------------------------------------------------------------------------------------------
-def ref_available(cuda=False):
-    return os.path.exists(REF_CUDA_BIN if cuda else REF_BIN)
+def ref_available(cuda=False, multislot=False):
+    return os.path.exists(REF_CUDA_MS_BIN if multislot else (REF_CUDA_BIN if cuda else REF_BIN))
 
 
 def write_mesh_files(dirname, tag, node, elem, etype, med, evol=None):
@@ -255,11 +256,12 @@ def write_mesh_files(dirname, tag, node, elem, etype, med, evol=None):
             f.write("%d %.9g %.9g %.9g %.9g\n" % (i + 1, m[0], m[1], m[2], m[3]))
 
 
-def run_ref(node, elem, etype, med, *, nthread=1, cuda=False, extra_args=(), timeout=3600, keep_dir=None, evol=None, check=True, **kw):
+def run_ref(node, elem, etype, med, *, nthread=1, cuda=False, extra_args=(), timeout=3600, keep_dir=None, evol=None, check=True,
+            expect="out.bin", multislot=False, **kw):
     """Run oracle/_ref/mmc_ref (or mmc_refcuda) on the same inputs; returns dict(field, absorbed_frac, speed, ...)."""
     p = dict(DEFAULTS)
     p.update(kw)
-    binp = REF_CUDA_BIN if cuda else REF_BIN
+    binp = REF_CUDA_MS_BIN if multislot else (REF_CUDA_BIN if cuda else REF_BIN)
     tmp = keep_dir or tempfile.mkdtemp(prefix="mmcref_")
     os.makedirs(tmp, exist_ok=True)
     tag = "t"
@@ -300,7 +302,7 @@ def run_ref(node, elem, etype, med, *, nthread=1, cuda=False, extra_args=(), tim
     env = dict(os.environ, OMP_NUM_THREADS=str(nthread))
     r = subprocess.run(args, cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout)
     log = r.stdout.decode(errors="replace")
-    if r.returncode != 0 and (check or not os.path.exists(os.path.join(tmp, "out.bin"))):     # check=False: results were saved before a crash at exit
+    if r.returncode != 0 and (check or not os.path.exists(os.path.join(tmp, expect))):     # check=False: results (`expect`) were saved before a crash at exit
         raise RuntimeError("reference failed (%d): %s\n%s" % (r.returncode, " ".join(args), log[-3000:]))
     out = dict(log=log, dir=tmp)
     m = re.search(r"total simulated energy:\s*([0-9.eE+-]+)\s*absorbed:\s*(?:\x1b\[[0-9;]*m)*([0-9.eE+-]+)%", log)
