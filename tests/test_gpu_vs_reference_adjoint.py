@@ -36,16 +36,19 @@ def _stats(ours, ref, lit_frac):
     return int(lit.sum()), float(np.median(rel)), float(np.percentile(rel, 90)), float(ours[lit].sum() / ref[lit].sum()), cc
 
 
-def _ref_jacobians(method, basisorder, N, tmp):
+def _ref_jacobians(method, basisorder, N, tmp, flag="w", omega=0.0):
     node, elem, et, med = cases.two_media_cube()
     kw = dict(nphoton=N, seed=1648335518, srcpos=(10.1, 10.2, 0.0), srcdir=(0, 0, 1), tstart=0.0, tend=5e-9, tstep=5e-9, isreflect=1,
               method=method, basisorder=basisorder, steps=1.0, detpos=DETS,
               e0=int(mmc.mesh_initelem(node, elem, (10.1, 10.2, 0.0))[0]))
+    overlay = OVERLAY
+    if omega:       # one -j fragment only (the last one wins, src/mmc_utils.c:4088-4097); it resets the gates it does not name
+        overlay = json.dumps(dict(json.loads(OVERLAY), Forward={"T0": 0, "T1": 5e-9, "Dt": 5e-9, "N0": 1, "Omega": omega}))
     r = orc.run_ref(node, elem, et, med, cuda=True, multislot=True, timeout=600, check=False, keep_dir=str(tmp), expect="out_jmua.jnii",
-                    extra_args=["-O", "w", "-F", "jnii", "-j", OVERLAY], **kw)
+                    extra_args=["-O", flag, "-F", "jnii", "-j", overlay], **kw)
     from mmc_b200 import volio
     jm = volio.loadjnii(os.path.join(str(tmp), "out_jmua.jnii"))["vol"]
-    jd = volio.loadjnii(os.path.join(str(tmp), "out_jd.jnii"))["vol"]
+    jd = volio.loadjnii(os.path.join(str(tmp), "out_jd.jnii"))["vol"] if flag == "w" else np.zeros(0)
     return (node, elem, et, med, kw), r, np.asarray(jm, np.float64), np.asarray(jd, np.float64)
 
 
@@ -97,3 +100,26 @@ def test_mesh_adjoint_jacobians_vs_reference_cuda(tmp_path):
         print("mesh J_D   pair %d: %d strong nodes, median %.4f, p90 %.4f, sum ratio %.5f, corr %.5f" % (pair, n, med_, p90, ratio, cc))
         assert n > 5
         assert med_ < 0.10 and abs(ratio - 1) < 0.05 and cc > 0.98, (med_, p90, ratio, cc)
+
+
+@needs_refcuda
+def test_grid_rf_adjoint_jmua_vs_reference_cuda(tmp_path):
+    """RF run (omega = 2 pi 200 MHz): the complex J_mua = -V phi_s phi_d is the one output of the reference program that carries the
+    IMAGINARY fluence (mesh_saveweight drops it, mesh_savejacob writes [Re, Im] on a trailing axis, src/mmc_mesh.c:1886-1925), so
+    this pins the imaginary part of the complex deposit (src/mmc_core.cl:1043-1078) against the reference's own kernel."""
+    N = 20000000
+    omega = 2 * np.pi * 2e8
+    (node, elem, et, med, kw), r, jm, _ = _ref_jacobians(cases.GRID, 0, N, tmp_path, flag="a", omega=omega)
+    g = mmc.run(dict(node=node, elem=elem, elemprop=et, prop=np.vstack([[0, 0, 1, 1], med]), method="grid", steps=(1.0, 1.0, 1.0),
+                     outputtype="adjoint", detdir=DETDIR, omega=omega, **{k: v for k, v in kw.items() if k not in ("method", "steps")}))
+    J = g["jacob"]                              # [Re J_mua, Im J_mua][pair][voxel]
+    jm = jm.reshape(2, 2, -1)                   # [Re, Im][pair][voxel]
+    assert J.shape == jm.shape, (J.shape, jm.shape)
+    for part, name in ((0, "Re"), (1, "Im")):
+        for pair in range(2):
+            n, med_, p90, ratio, cc = _stats(J[part][pair], jm[part][pair], 1e-2)
+            print("RF grid %s J_mua pair %d: %d lit voxels, median %.4f, p90 %.4f, sum ratio %.5f, corr %.5f" % (name, pair, n, med_, p90, ratio, cc))
+            assert n > 50
+            assert med_ < 0.05 and p90 < 0.15 and abs(ratio - 1) < 0.02 and cc > 0.995, (name, pair, med_, p90, ratio, cc)
+    # the imaginary part is a real signal, not noise around zero
+    assert np.abs(jm[1]).max() > 0.05 * np.abs(jm[0]).max()
