@@ -219,6 +219,19 @@ extern "C" void mmc_run_cu(mcconfig* cfg, tetmesh* mesh, raytracer* tracer) {
 
     // ---- outputs (ownership as in src/mmc_cu_host.cu:339-367: exportfield defaults to mesh->weight; detected rows and
     //      seeds are malloc'ed here and freed by the caller)
+#ifndef MCX_CONTAINER
+
+    // The stock command-line host sizes mesh->weight for cfg->srcnum sources when the mesh is loaded (src/mmc_mesh.c:654,688) and
+    // appends the detector / multi-source slots only later (mcx_prep, src/mmc_utils.c:3760-3797), so an adjoint run of the stock
+    // program writes past the buffer.  Give the volume its real size here, as mesh_validate does for the containers
+    // (src/mmc_mesh.c:2389-2394).
+    if (cfg->exportfield == NULL && cfg->parentid == mpStandalone && sz.nslots > 1) {
+        free(mesh->weight);
+        mesh->weight = (double*)calloc(sz.fieldlen, sizeof(double));
+    }
+
+#endif
+
     if (cfg->exportfield == NULL) {
         cfg->exportfield = mesh->weight;
     }

@@ -47,3 +47,53 @@ def test_reference_cli_drives_the_b200_engine(bench):
     assert cpu.returncode == 0, cpu.stdout[-2000:] + cpu.stderr[-2000:]
     fg, fc = _absorbed(gpu.stdout), _absorbed(cpu.stdout)
     assert abs(fg - fc) < 2.5e-3, (fg, fc)          # 1e6 photons: sigma ~ 4e-4
+
+
+@needs_cli
+@pytest.mark.gpu
+def test_reference_cli_writes_adjoint_jacobians_through_the_b200_engine(tmp_path):
+    """`-O w` (J_mua + J_D) through the unmodified reference command line: input parsing, mcx_prep's detector slots, mesh_savejacob's
+    JNIfTI files are the reference's; the engine and the post-kernels are ours.  The stock program cannot finish this run (it sizes its
+    volume before the slots exist, see tests/test_gpu_vs_reference_adjoint.py); the stub re-sizes it.  The files must hold what the
+    Python host returns for the same problem and seed: same engine, same host seed stream, so the agreement is to rounding."""
+    import json
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cases
+    import mmc_b200 as mmc
+    import orc
+    from mmc_b200 import volio
+    node, elem, et, med = cases.two_media_cube()
+    dets = [(10.3, 8.4, 0.0, 1.0), (11.7, 12.4, 20.0, 1.0)]
+    detdir = [(0, 0, 1, 0), (0, 0, -1, 0)]
+    e0 = int(mmc.mesh_initelem(node, elem, (10.1, 10.2, 0.0))[0])
+    kw = dict(nphoton=1000000, seed=1648335518, srcpos=(10.1, 10.2, 0.0), srcdir=(0, 0, 1), tstart=0.0, tend=5e-9, tstep=5e-9, isreflect=1,
+              basisorder=0, detpos=dets, e0=e0)
+    orc.write_mesh_files(str(tmp_path), "t", node, elem, et, med, None)
+    with open(os.path.join(str(tmp_path), "in.inp"), "w") as f:
+        f.write("1000000\n1648335518\n10.1 10.2 0\n0 0 1 0\n0 5e-9 5e-9\nt\n%d\n2 1\n" % e0)
+        for d in dets:
+            f.write("%.9g %.9g %.9g %.9g\n" % d)
+    overlay = json.dumps({"Optode.Detector": 1, "Optode.Detector.Dir": [list(d) for d in detdir]})
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([CLI, "-f", "in.inp", "-s", "out", "-M", "g", "--gridsize", "1", "-b", "1", "-C", "0", "-U", "1", "-O", "w", "-F", "jnii",
+                        "-D", "T", "-S", "1", "-n", "1000000", "-E", "1648335518", "-c", "cuda", "-G", "1", "-j", overlay],
+                       capture_output=True, text=True, timeout=300, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MMC-B200" in r.stdout
+    jm = volio.loadjnii(os.path.join(str(tmp_path), "out_jmua.jnii"))["vol"].reshape(2, -1)
+    jd = volio.loadjnii(os.path.join(str(tmp_path), "out_jd.jnii"))["vol"].reshape(2, -1)
+    g = mmc.run(dict(node=node, elem=elem, elemprop=et, prop=np.vstack([[0, 0, 1, 1], med]), method="grid", steps=(1.0, 1.0, 1.0),
+                     outputtype="adjointmuad", detdir=detdir, **kw))
+    J = g["jacob"]
+    assert jm.shape == J[0].shape and np.abs(jm).max() > 0 and np.abs(jd).max() > 0
+    # both are Monte Carlo runs of the same engine; the thread-to-photon assignment of the dynamic pool is not reproducible, so the
+    # comparison is statistical at 1e6 photons (bright voxels)
+    for ours, ref, name in ((J[0], jm, "J_mua"), (J[1], jd, "J_D")):
+        for pair in range(2):
+            lit = np.abs(ref[pair]) > 0.05 * np.abs(ref[pair]).max()
+            rel = np.abs(ours[pair][lit] - ref[pair][lit]) / np.abs(ref[pair][lit])
+            cc = np.corrcoef(ours[pair], ref[pair])[0, 1]
+            print("%s pair %d: %d voxels, median %.4f, corr %.5f" % (name, pair, lit.sum(), np.median(rel), cc))
+            assert lit.sum() > 5 and np.median(rel) < 0.15 and cc > 0.97, (name, pair, np.median(rel), cc)
