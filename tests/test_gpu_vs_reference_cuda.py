@@ -106,3 +106,49 @@ def test_rf_real_part_vs_reference_cuda_1e7():
     dcw = np.median(np.abs(cwv[lit] - ref[lit]) / np.abs(ref[lit]))
     print("CW vs RF real part: median %.4f" % dcw)
     assert dcw > 0.01 and dcw > 4 * np.median(rel)
+
+
+@needs_refcuda
+@pytest.mark.parametrize("otype", ["wl", "wp", "jacobian"])
+def test_replay_outputs_vs_reference_cuda(otype, tmp_path):
+    """BASELINE config C5 flow (examples/replaywide) against the reference's own kernel: planar source, wide-field detector, run 1
+    (this engine) writes init.mch with the detected photons and their seeds, run 2 is `-E init.mch -P 0 -O L|P|J` in BOTH programs.
+    A replayed photon restarts from its saved xorshift128+ state, so both kernels follow the same trajectories up to fp rounding and
+    the comparison is nearly deterministic: it pins the GPU replay semantics (src/mmc_core.cl:814-829; `-O J` accumulates the path
+    length on the GPU where the CPU file uses exp(-DELTA_MUA L)) and mesh_loadseedfile's weights
+    (src/mmc_mesh.c:855-891) through the .mch file this engine wrote.  One medium: for maxmedia > 1 the reference reads the partial
+    paths from the wrong columns (see mmc_b200/mch.py: replay_inputs)."""
+    from mmc_b200 import mch
+    from test_gpu_parity import _cfg
+    node, elem, et, med = cases.case_mesh("planar_widedet")
+    kw = cases.case_kwargs("planar_widedet")
+    kw.update(nphoton=200000, issaveseed=1)
+    first = mmc.run(_cfg(node, elem, et, med, **kw))
+    assert len(first["detp"]) > 10000
+    f = str(tmp_path / "init.mch")
+    mch.savemch(f, first["detp"], first["seeds"], maxmedia=len(med), totalphoton=kw["nphoton"], normalizer=first["normalizer"])
+    rp = mch.replay_inputs(mch.loadmch(f), np.vstack([[0, 0, 1, 1], med]))
+    n = rp["nphoton"]
+    kw2 = {k: v for k, v in kw.items() if k not in ("seed", "nphoton", "issaveseed")}
+    kw2.update(outputtype={"wl": cases.WL, "wp": cases.WP, "jacobian": cases.JACOBIAN}[otype], minenergy=0.0, isnormalized=0)
+    r = orc.run_ref(node, elem, et, med, cuda=True, timeout=300, keep_dir=str(tmp_path), nphoton=n, seed=1,
+                    extra_args=["-E", "init.mch", "-P", "0"], **kw2)
+    cfg = _cfg(node, elem, et, med, **kw2)
+    cfg.update(replayseed=rp["replayseed"], replayweight=rp["replayweight"], replaytime=rp["replaytime"])
+    g = mmc.run(cfg)
+    ours = g["raw"][..., 0]
+    ref = r["field_flat"].reshape(ours.shape)
+    ours, ref = np.where(np.isfinite(ours), ours, 0), np.where(np.isfinite(ref), ref, 0)
+    tot = ours.sum() / ref.sum()
+    cw_o, cw_r = ours.sum(axis=0), ref.sum(axis=0)
+    lit = cw_r > 1e-3 * cw_r.max()
+    rel = np.abs(cw_o[lit] - cw_r[lit]) / cw_r[lit]
+    print("replay %s vs reference CUDA: %d photons, total ratio %.6f, %d lit elements, median %.2e, p99 %.2e, max %.2e"
+          % (otype, n, tot, lit.sum(), np.median(rel), np.percentile(rel, 99), rel.max()))
+    assert lit.sum() > 500
+    assert abs(tot - 1) < 2e-3, tot
+    assert np.median(rel) < 5e-3 and np.percentile(rel, 99) < 0.05, (np.median(rel), np.percentile(rel, 99))
+    # per gate as well
+    go, gr = ours.sum(axis=1), ref.sum(axis=1)
+    big = gr > 1e-3 * gr.max()
+    np.testing.assert_allclose(go[big], gr[big], rtol=5e-3)
