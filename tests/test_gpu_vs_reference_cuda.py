@@ -117,7 +117,8 @@ def test_replay_outputs_vs_reference_cuda(otype, tmp_path):
     the comparison is nearly deterministic: it pins the GPU replay semantics (src/mmc_core.cl:814-829; `-O J` accumulates the path
     length on the GPU where the CPU file uses exp(-DELTA_MUA L)) and mesh_loadseedfile's weights
     (src/mmc_mesh.c:855-891) through the .mch file this engine wrote.  One medium: for maxmedia > 1 the reference reads the partial
-    paths from the wrong columns (see mmc_b200/mch.py: replay_inputs)."""
+    paths from the wrong columns (see mmc_b200/mch.py: replay_inputs).  (`-O F` with a seed file is not an option: the reference host
+    uploads cfg->replayweight, which mesh_loadseedfile only builds for L|P|J: "invalid argument", src/mmc_cu_host.cu:596-598.)"""
     from mmc_b200 import mch
     from test_gpu_parity import _cfg
     node, elem, et, med = cases.case_mesh("planar_widedet")
