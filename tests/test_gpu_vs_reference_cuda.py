@@ -153,3 +153,17 @@ def test_replay_outputs_vs_reference_cuda(otype, tmp_path):
     go, gr = ours.sum(axis=1), ref.sum(axis=1)
     big = gr > 1e-3 * gr.max()
     np.testing.assert_allclose(go[big], gr[big], rtol=5e-3)
+    # the replayed photons are detected again (matlab/mmcjmua.m:55-60): the reference's out.mch and our rows hold the same photons.
+    # Rows come in launch order on neither side, so they are paired by nearest neighbour over all columns (detector element, scattering
+    # count, partial path, exit position and direction, initial weight).
+    if otype == "wl" and "mch" in r:
+        from scipy.spatial import cKDTree
+        rd, gd = mch.loadmch(r["mch"])["detp"], g["detp"]
+        assert rd.shape[1] == gd.shape[1], (rd.shape, gd.shape)
+        assert abs(len(rd) - len(gd)) <= 0.005 * n and abs(len(gd) - n) <= 0.02 * n, (len(rd), len(gd), n)
+        scale = np.maximum(np.abs(rd).max(axis=0), 1e-6)
+        dist, idx = cKDTree(gd / scale).query(rd / scale)
+        close = dist < 1e-4
+        print("replayed rows: reference %d, ours %d, paired within 1e-4 of the column ranges: %.4f, distinct partners %.4f"
+              % (len(rd), len(gd), close.mean(), len(np.unique(idx[close])) / max(close.sum(), 1)))
+        assert close.mean() > 0.97 and len(np.unique(idx[close])) > 0.99 * close.sum()
