@@ -66,7 +66,7 @@ def loadmch(path):
                 srcnum=srcnum, respin=respin, savedetflag=savedetflag, detp=detp, seeds=seeds)
 
 
-def replay_inputs(mch, prop, replaydet=0):
+def replay_inputs(mch, prop, replaydet=0, legacy_columns=False):
     """mesh_loadseedfile (src/mmc_mesh.c:855-891): select the photons of detector `replaydet` (0 = all) and compute
     replayweight = w0 * prod_j exp(-mua_j * ppath_j * unitinmm) and replaytime = sum_j n_j * ppath_j * R_C0.
 
@@ -74,14 +74,15 @@ def replay_inputs(mch, prop, replaydet=0):
     row, i.e. it assumes ONE scattering-count column before the partial paths (the legacy MCX layout); rows written by
     MMC carry maxmedia scattering-count columns, so for maxmedia > 1 the reference reads the wrong columns.  This
     helper reads the partial-path columns where MMC writes them (1+M .. 2M), which coincides with the reference for
-    maxmedia == 1."""
+    maxmedia == 1.  legacy_columns=True reads columns 2 .. maxmedia+1 exactly like the reference does (used by the parity test that
+    replays a two-media run in both programs: the weights are then equally "wrong" on both sides and the trajectories must coincide)."""
     if mch["seeds"] is None:
         raise ValueError("the history file carries no seeds (run with issaveseed=1)")
     prop = np.asarray(prop, dtype=np.float32).reshape(-1, 4)
     M = int(mch["maxmedia"])
     d = mch["detp"]
     sel = np.ones(len(d), bool) if replaydet == 0 else (d[:, 0].astype(np.int64) == int(replaydet))
-    pp = d[sel, 1 + M:1 + 2 * M]
+    pp = d[sel, 2:2 + M] if legacy_columns else d[sel, 1 + M:1 + 2 * M]
     w = d[sel, -1].astype(np.float32).copy()
     t = np.zeros(len(w), dtype=np.float32)
     for j in range(M):

@@ -109,7 +109,7 @@ def test_rf_real_part_vs_reference_cuda_1e7():
 
 
 @needs_refcuda
-@pytest.mark.parametrize("otype", ["wl", "wp", "jacobian"])
+@pytest.mark.parametrize("otype", ["wl", "wp", "jacobian", "wl-twomedia"])
 def test_replay_outputs_vs_reference_cuda(otype, tmp_path):
     """BASELINE config C5 flow (examples/replaywide) against the reference's own kernel: planar source, wide-field detector, run 1
     (this engine) writes init.mch with the detected photons and their seeds, run 2 is `-E init.mch -P 0 -O L|P|J` in BOTH programs.
@@ -121,17 +121,22 @@ def test_replay_outputs_vs_reference_cuda(otype, tmp_path):
     uploads cfg->replayweight, which mesh_loadseedfile only builds for L|P|J: "invalid argument", src/mmc_cu_host.cu:596-598.)"""
     from mmc_b200 import mch
     from test_gpu_parity import _cfg
-    node, elem, et, med = cases.case_mesh("planar_widedet")
-    kw = cases.case_kwargs("planar_widedet")
-    kw.update(nphoton=200000, issaveseed=1)
+    # wl-twomedia: the cube with an inclusion of another refractive index (1.37 / 1.5, g = 0.01 / 0.9) and two point detectors, so the
+    # replayed trajectories go through refraction at an INTERNAL boundary and forward-peaked scattering.  The reference reads the
+    # partial paths of a maxmedia = 2 file from the wrong columns; legacy_columns gives this engine the same (mis-)weights.
+    case = "blb_detectors" if otype == "wl-twomedia" else "planar_widedet"
+    node, elem, et, med = cases.case_mesh(case)
+    kw = cases.case_kwargs(case)
+    kw.update(nphoton=400000 if otype == "wl-twomedia" else 200000, issaveseed=1)
     first = mmc.run(_cfg(node, elem, et, med, **kw))
     assert len(first["detp"]) > 10000
     f = str(tmp_path / "init.mch")
-    mch.savemch(f, first["detp"], first["seeds"], maxmedia=len(med), totalphoton=kw["nphoton"], normalizer=first["normalizer"])
-    rp = mch.replay_inputs(mch.loadmch(f), np.vstack([[0, 0, 1, 1], med]))
+    mch.savemch(f, first["detp"], first["seeds"], maxmedia=len(med), totalphoton=kw["nphoton"], normalizer=first["normalizer"],
+                detnum=len(kw.get("detpos", [])))
+    rp = mch.replay_inputs(mch.loadmch(f), np.vstack([[0, 0, 1, 1], med]), legacy_columns=(otype == "wl-twomedia"))
     n = rp["nphoton"]
     kw2 = {k: v for k, v in kw.items() if k not in ("seed", "nphoton", "issaveseed")}
-    kw2.update(outputtype={"wl": cases.WL, "wp": cases.WP, "jacobian": cases.JACOBIAN}[otype], minenergy=0.0, isnormalized=0)
+    kw2.update(outputtype={"wl": cases.WL, "wp": cases.WP, "jacobian": cases.JACOBIAN, "wl-twomedia": cases.WL}[otype], minenergy=0.0, isnormalized=0)
     r = orc.run_ref(node, elem, et, med, cuda=True, timeout=300, keep_dir=str(tmp_path), nphoton=n, seed=1,
                     extra_args=["-E", "init.mch", "-P", "0"], **kw2)
     cfg = _cfg(node, elem, et, med, **kw2)
@@ -140,13 +145,28 @@ def test_replay_outputs_vs_reference_cuda(otype, tmp_path):
     ours = g["raw"][..., 0]
     ref = r["field_flat"].reshape(ours.shape)
     ours, ref = np.where(np.isfinite(ours), ours, 0), np.where(np.isfinite(ref), ref, 0)
+    if otype == "wl-twomedia":
+        # Every replayed photon of the pencil beam deposits in the launch element during the first microseconds of the run.  The
+        # reference accumulates in float with its MAX_ACCUM spill protocol (src/mmc_core.cl:352,904-912) and comes out ~5 % short on
+        # that one accumulator (measured: 22 553 against 23 787), while this engine (fp64 red) agrees with the double-precision CPU
+        # oracle on the same seeds to 4e-6.  The launch element is therefore checked against the oracle and left out of the
+        # comparison with the reference kernel.
+        hot = int(mmc.mesh_initelem(node, elem, kw["srcpos"])[0]) - 1
+        o = orc.run(node, elem, et, med, nthread=8, gpu_semantics=1, seed=orc.SEED_FROM_FILE, nphoton=n, photonseed=rp["replayseed"],
+                    replayweight=rp["replayweight"], replaytime=rp["replaytime"], **kw2)
+        fo = np.where(np.isfinite(o["field"][..., 0]), o["field"][..., 0], 0)
+        print("launch element %d: ours %.2f, CPU oracle %.2f, reference CUDA %.2f" % (hot + 1, ours[:, hot].sum(), fo[:, hot].sum(), ref[:, hot].sum()))
+        assert abs(ours[:, hot].sum() / fo[:, hot].sum() - 1) < 2e-3
+        assert abs(ours.sum() / fo.sum() - 1) < 2e-3
+        ours[:, hot] = 0
+        ref[:, hot] = 0
     tot = ours.sum() / ref.sum()
     cw_o, cw_r = ours.sum(axis=0), ref.sum(axis=0)
     lit = cw_r > 1e-3 * cw_r.max()
     rel = np.abs(cw_o[lit] - cw_r[lit]) / cw_r[lit]
     print("replay %s vs reference CUDA: %d photons, total ratio %.6f, %d lit elements, median %.2e, p99 %.2e, max %.2e"
           % (otype, n, tot, lit.sum(), np.median(rel), np.percentile(rel, 99), rel.max()))
-    assert lit.sum() > 500
+    assert lit.sum() > (300 if otype == "wl-twomedia" else 500)
     assert abs(tot - 1) < 2e-3, tot
     assert np.median(rel) < 5e-3 and np.percentile(rel, 99) < 0.05, (np.median(rel), np.percentile(rel, 99))
     # per gate as well
@@ -156,14 +176,22 @@ def test_replay_outputs_vs_reference_cuda(otype, tmp_path):
     # the replayed photons are detected again (matlab/mmcjmua.m:55-60): the reference's out.mch and our rows hold the same photons.
     # Rows come in launch order on neither side, so they are paired by nearest neighbour over all columns (detector element, scattering
     # count, partial path, exit position and direction, initial weight).
-    if otype == "wl" and "mch" in r:
+    if otype in ("wl", "wl-twomedia") and "mch" in r:
         from scipy.spatial import cKDTree
         rd, gd = mch.loadmch(r["mch"])["detp"], g["detp"]
         assert rd.shape[1] == gd.shape[1], (rd.shape, gd.shape)
         assert abs(len(rd) - len(gd)) <= 0.005 * n and abs(len(gd) - n) <= 0.02 * n, (len(rd), len(gd), n)
-        scale = np.maximum(np.abs(rd).max(axis=0), 1e-6)
+        scale = np.maximum(np.abs(rd).max(axis=0), 1.0)     # floor: the exit z of a detector at z = 0 is rounding noise around 0
         dist, idx = cKDTree(gd / scale).query(rd / scale)
         close = dist < 1e-4
         print("replayed rows: reference %d, ours %d, paired within 1e-4 of the column ranges: %.4f, distinct partners %.4f"
               % (len(rd), len(gd), close.mean(), len(np.unique(idx[close])) / max(close.sum(), 1)))
+        if close.mean() < 0.97:     # which columns disagree?  pair on exit position + direction only
+            d2, i2 = cKDTree(gd[:, -7:-1]).query(rd[:, -7:-1])
+            ok = d2 < 1e-3
+            bad = np.abs(gd[i2[ok]] - rd[ok]) > 1e-3 * scale
+            print("  paired on exit position/direction: %.4f; share of pairs whose column differs: %s" % (ok.mean(), np.round(bad.mean(axis=0), 3)))
+            k = np.nonzero(bad.any(axis=1))[0][:3]
+            for q in k:
+                print("   ref ", np.round(rd[ok][q], 4), "\n   ours", np.round(gd[i2[ok]][q], 4))
         assert close.mean() > 0.97 and len(np.unique(idx[close])) > 0.99 * close.sum()
