@@ -950,8 +950,13 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
 #ifndef MMCB_MINBLOCKS_HP
 #define MMCB_MINBLOCKS_HP 5      // measured: 4 -> 5 CTAs per SM +2 % (cube60) .. +8 % (sphshells), profiles/r1j_tune_hp_occupancy.jsonl
 #endif
+#ifndef MMCB_MINBLOCKS_HAVEL
+#define MMCB_MINBLOCKS_HAVEL 7   // the Havel kernel is latency-bound (65 % issue slots busy, two dependent gathers per step): 7 CTAs per SM at 72
+                                 // registers, no spills: cube60 45.5 -> 44.0 ms, sphshells 202 -> 193 ms; 8 CTAs (64 registers) spill and lose;
+                                 // Plucker is indifferent; the detector / general-source variants would spill at 72 and keep 5 (profiles/r1l_tune_hp_occupancy.jsonl)
+#endif
 template <int METHOD, bool DET, bool GENERAL, bool RF = false>
-__global__ void __launch_bounds__((METHOD <= 1) ? MMCB_MAXTHREADS_HP : MMCB_MAXTHREADS, (METHOD <= 1) ? MMCB_MINBLOCKS_HP : MMCB_MINBLOCKS)
+__global__ void __launch_bounds__((METHOD <= 1) ? MMCB_MAXTHREADS_HP : MMCB_MAXTHREADS, (METHOD == 1 && !DET && !GENERAL) ? MMCB_MINBLOCKS_HAVEL : ((METHOD <= 1) ? MMCB_MINBLOCKS_HP : MMCB_MINBLOCKS))
 mmcb_photon_kernel(const mmcb_kargs a) {
     static_assert(!RF || (GENERAL && METHOD >= 3), "RF forward runs use the general branch-less Badouel kernels");
     constexpr bool GRID = (METHOD == 4);

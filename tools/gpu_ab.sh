@@ -2,7 +2,7 @@
 # A/B of library variants under build/variants (GPU box): one short bench line per variant and workload
 # usage: tools/gpu_ab.sh TAG "variant ..." "workload:method ..."
 O=gpurun_out; mkdir -p $O; TAG=${1:-ab}; VARS=${2:-"base"}; WLS=${3:-"sphshells:grid"}
-for rep in 1 2; do
+for rep in $(seq 1 ${REPS:-2}); do
 for v in $VARS; do
   if [ "$v" = product ]; then LIB=mmc_b200/libmmc_b200.so; else LIB=build/variants/libmmc_b200_$v.so; fi
   for wl in $WLS; do
