@@ -331,7 +331,7 @@ def main():
     if e2e is not None:
         line["e2e"] = e2e
 
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU leg is timed at N=1 only (rank 0); larger runs carry the GPU numbers alone
         threads = os.cpu_count() or 1
         c = cpu_reference_run(cfg, int(args.ref_photons), threads)
         line["cpu_baseline"] = {"value": c["value"], "unit": "photons/ms", "cores": threads, "kind": c["kind"],
