@@ -43,6 +43,16 @@ def test_mch_round_trip_and_replay_inputs(tmp_path):
     np.testing.assert_allclose(r["replayweight"], w, rtol=1e-5)
     np.testing.assert_allclose(r["replaytime"], t, rtol=1e-5)
 
+    # legacy_columns: the columns mesh_loadseedfile itself reads, j = 2 .. maxmedia+1 (src/mmc_mesh.c:874-882); for maxmedia = 2 that is
+    # (nscat_2, ppath_1) -- the reference's own (mis-)weights, needed to replay a multi-media file in both programs on equal terms
+    rl = mch.replay_inputs(h, prop, replaydet=2, legacy_columns=True)
+    wl = (detp[sel, -1] * np.exp(-prop[1, 0] * detp[sel, 2]) * np.exp(-prop[2, 0] * detp[sel, 3])).astype(np.float32)
+    np.testing.assert_allclose(rl["replayweight"], wl, rtol=1e-6)
+    np.testing.assert_allclose(rl["replaytime"], (prop[1, 3] * detp[sel, 2] + prop[2, 3] * detp[sel, 3]) * mch.R_C0, rtol=1e-6)
+    one = mch.replay_inputs(dict(h, maxmedia=1, detp=detp[:, [0, 1, 3, 4]]), prop[:2])      # maxmedia == 1: both readings coincide
+    leg = mch.replay_inputs(dict(h, maxmedia=1, detp=detp[:, [0, 1, 3, 4]]), prop[:2], legacy_columns=True)
+    assert np.array_equal(one["replayweight"], leg["replayweight"]) and np.array_equal(one["replaytime"], leg["replaytime"])
+
 
 def test_bin_round_trip(tmp_path):
     a = np.arange(24, dtype=np.float64).reshape(3, 8)
