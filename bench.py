@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--workload", default="sphshells")
     ap.add_argument("--method", default=None)
     ap.add_argument("--photons", type=float, default=1e7)
-    ap.add_argument("--ref-photons", type=float, default=2e5)
+    ap.add_argument("--ref-photons", type=float, default=1e6)      # ~6 s of CPU work per sample at 16 host threads (the reference CPU path runs this workload at 0.15-0.27 k photons/ms)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
