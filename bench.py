@@ -295,7 +295,8 @@ def main():
         # the centroids are built on the device.  D2H: the volume + the raw face-neighbour table (numbered on the host)
         h2d = ne * 16 * 2 + ne * 16 + ne * 4 + nn * 12 + 16 * nthread
         e2e = {"value": world * nphoton * reps / float(tt[0]), "unit": "photons/ms", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(r["raw"].size * 8 + ne * 16), "ms": float(tt[0]) / reps, "kernel_ms": float(np.mean(e2e_kern)), "runs": reps}
+               "d2h_bytes_per_step": int(r["raw"].size * 8 + ne * 16), "ms": float(tt[0]) / reps, "kernel_ms": float(np.mean(e2e_kern)), "runs": reps,
+               "ms_runs": [round(x, 2) for x in e2e_ms]}
 
     if rank != 0:
         if dist is not None:
