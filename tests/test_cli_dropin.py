@@ -97,3 +97,26 @@ def test_reference_cli_writes_adjoint_jacobians_through_the_b200_engine(tmp_path
             cc = np.corrcoef(ours[pair], ref[pair])[0, 1]
             print("%s pair %d: %d voxels, median %.4f, corr %.5f" % (name, pair, lit.sum(), np.median(rel), cc))
             assert lit.sum() > 5 and np.median(rel) < 0.15 and cc > 0.97, (name, pair, np.median(rel), cc)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference headers (this container only)")
+@pytest.mark.parametrize("flavour", [[], ["-DMCX_CONTAINER"]])
+def test_stub_compiles_against_the_reference_headers(flavour, tmp_path):
+    """integration/mmc_cu_host_b200.cpp against the reference's own headers, as the stand-alone program builds it and as the
+    mmclab / pmmc containers do (MCX_CONTAINER: no file output, errors as exceptions).  It must export exactly the two symbols the
+    reference host links against (src/mmc_cu_host.h:46-62) and pull nothing but the C-ABI from this repository."""
+    ref = "/root/reference/src"
+    clh = tmp_path / "mmc_core.clh"
+    clh.write_text("unsigned char mmc_core_cl[] = {0};\n")
+    obj = str(tmp_path / "stub.o")
+    cmd = ["g++", "-c", "-std=c++11", "-O1", "-w", "-fopenmp", "-msse4.1", "-DUSE_OS_TIMER", "-DMMC_XORSHIFT", "-DMCX_EMBED_CL", "-DMMC_USE_SSE",
+           "-DHAVE_SSE2", "-DUSE_CUDA"] + flavour + ["-I", str(tmp_path), "-I", ref, "-I", ref + "/ubj", "-I", ref + "/zmat",
+           "-I", os.path.join(ROOT, "include"), "-o", obj, os.path.join(ROOT, "integration", "mmc_cu_host_b200.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    nm = subprocess.run(["nm", "-C", obj], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in nm.splitlines() if " T " in l}
+    assert {"mmc_run_cu", "mcx_list_cu_gpu"} <= exported, exported
+    ours = {l.split()[-1] for l in nm.splitlines() if " U " in l and l.split()[-1].startswith("mmcb_")}
+    hdr = open(os.path.join(ROOT, "include", "mmc_b200.h")).read()
+    assert ours and all(re.search(r"\b%s\s*\(" % s, hdr) for s in ours), ours
