@@ -21,10 +21,11 @@
 
 // kernel-side launchers (mmcb_kernel.cu)
 extern "C" int mmcb_k_upload_param(const mmcb_kparam* hp, const float* det4, int detnum, cudaStream_t st);
-extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int carveout,
+extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int carveout, int repack,
                                      cudaStream_t st);
-extern "C" int mmcb_k_max_block(int method);
-extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int* blocks_per_sm);
+extern "C" int mmcb_k_max_block(int method, int repack);
+extern "C" size_t mmcb_k_rp_smem(int block, int isdet, int devreclen);
+extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int repack, int* blocks_per_sm);
 // mesh pre-processing on the device (mmcb_prep.cu)
 extern "C" int mmcb_k_facenb(const int* d_elem, int ne, int* d_facenb, cudaStream_t st);
 extern "C" int mmcb_k_build_records(const float* d_node, const int* d_elem, const int* d_facenb, const int* d_type, const float* d_med_n, int ne,
@@ -994,6 +995,7 @@ struct mmcb_session {
     int grid = 0, block = 128, nthread = 0;
     size_t smem = 0;
     bool isgrid = false, ishp = false, isdet = false, isgeneral = false;
+    bool repack = false;           // lane re-packing kernel (mmcb_kernel_rp.cuh): two walkers (RNG streams) per thread
     size_t fieldlen = 0, efieldlen = 0;     // output volume / kernel accumulator volume (differ for nodal BLB)
     bool acc_double = true, field_external = false;
     // device allocations
@@ -1143,6 +1145,12 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     s->isdet = c.issavedet != 0;
     s->isgeneral = !(c.srctype == MMCB_SRC_PENCIL || c.srctype == MMCB_SRC_ISOTROPIC) || c.srcnum > 1 ||
                    c.seed == MMCB_SEED_FROM_FILE || c.savetraj || c.issaveref || s->cfg.multisrc || s->cfg.isrf || c.nodemua != NULL;
+    // EXPERIMENTAL lane re-packing kernel (mmcb_kernel_rp.cuh), opt-in with MMCB_REPACK=1: measured SLOWER than the flattened kernel on
+    // every workload (profiles/r2a_repack_*), kept for the record and for its parity test.  It serves every single-pattern source;
+    // photon sharing, replay, trajectories, diffuse reflectance, multi-slot sources, RF and per-node optical properties change the
+    // step itself and stay on the flattened kernel, as do Havel / Plucker and the static (reference) schedule
+    s->repack = !s->ishp && c.schedule != 1 && getenv("MMCB_REPACK") && atoi(getenv("MMCB_REPACK")) > 0 &&
+                !(c.srcnum > 1 || c.seed == MMCB_SEED_FROM_FILE || c.savetraj || c.issaveref || s->cfg.multisrc || s->cfg.isrf || c.nodemua != NULL);
 
     // per-slot launch element (mesh_init_srcdata_eid, src/mmc_mesh.c:1114-1156): srcparam2.w of every slot that has none
     for (int slot = 0; slot < c.extrasrclen; slot++) {
@@ -1343,11 +1351,16 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     int smcount = 0, smemoptin = 0;       // two attributes instead of cudaGetDeviceProperties (several ms per call)
     CU(cudaDeviceGetAttribute(&smcount, cudaDevAttrMultiProcessorCount, device));
     CU(cudaDeviceGetAttribute(&smemoptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    s->block = (c.nblocksize > 0) ? std::min(c.nblocksize, mmcb_k_max_block(c.method)) : mmcb_k_max_block(c.method);
+    s->block = (c.nblocksize > 0) ? std::min(c.nblocksize, mmcb_k_max_block(c.method, s->repack)) : mmcb_k_max_block(c.method, s->repack);
     s->block = std::max(32, (s->block / 32) * 32);
     s->smem_base = 2 * sizeof(float4) * m.med.size() + (s->isdet ? sizeof(float) * (size_t)devreclen * s->block : 0);
     s->hot_allowed = (c.hotcache >= 0 && srcnum == 1);
     s->smem_scout = 2 * sizeof(float4) * m.med.size();
+
+    if (s->repack) {
+        s->smem_base = 2 * sizeof(float4) * m.med.size() + mmcb_k_rp_smem(s->block, s->isdet, devreclen);
+        s->smem_scout = 2 * sizeof(float4) * m.med.size() + mmcb_k_rp_smem(s->block, 0, 0);
+    }
     // the grid (= number of RNG streams) is sized for the larger footprint so that pilot and main launch share it
     s->smem = s->smem_base + (s->hot_allowed ? sizeof(unsigned int) * MMCB_HOT_SLOTS + sizeof(float) * MMCB_HOT_SLOTS * MMCB_HOT_GROUP : 0);
 
@@ -1364,7 +1377,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     }
 
     int bps = 0;
-    CUK(mmcb_k_occupancy(s->block, s->smem, c.method, s->isdet, s->isgeneral, s->cfg.isrf, &bps));
+    CUK(mmcb_k_occupancy(s->block, s->smem, c.method, s->isdet, s->isgeneral, s->cfg.isrf, s->repack, &bps));
 
     if (bps < 1) {
         return fail(MMCB_ERR_CUDA, "kernel cannot be resident with block=%d smem=%zu", s->block, s->smem);
@@ -1379,7 +1392,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
         s->grid = bps * smcount;
     }
 
-    s->nthread = s->grid * s->block;
+    s->nthread = s->grid * s->block * (s->repack ? 2 : 1);      // RNG streams: one per thread, two walkers per thread when re-packing
     CU(cudaMallocAsync(&s->d_seeds, sizeof(uint32_t) * 4 * (size_t)s->nthread, s->stream));
     // kernel parameters
     mmcb_kparam& k = s->kp;
@@ -1742,7 +1755,7 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
         ka.trajcount = ka.detcount + 1;
         CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
         CUK(mmcb_k_upload_param(&kp, s->cfg.detpos.data(), c.detnum, st));
-        CUK(mmcb_k_launch_photons(&ka, s->grid, s->block, s->smem_scout, c.method, 0, s->isgeneral, 0, s->carveout, st));
+        CUK(mmcb_k_launch_photons(&ka, s->grid, s->block, s->smem_scout, c.method, 0, s->isgeneral, 0, s->carveout, s->repack, st));
         CUK(mmcb_k_hot_select(scr, flen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys, c.hotcache > 0 ? 0.f : MMCB_HOT_MINSHARE, st));
         CU(cudaFreeAsync(scr, st));
         s->hot_ready = true;
@@ -1765,7 +1778,7 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
         kp.hotcache = (part == 1 && s->hot_ready) ? 1 : 0;
         CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
         CUK(mmcb_k_upload_param(&kp, s->cfg.detpos.data(), c.detnum, st));
-        CUK(mmcb_k_launch_photons(&s->ka, s->grid, s->block, kp.hotcache ? s->smem : s->smem_base, c.method, s->isdet, s->isgeneral, s->cfg.isrf, s->carveout, st));
+        CUK(mmcb_k_launch_photons(&s->ka, s->grid, s->block, kp.hotcache ? s->smem : s->smem_base, c.method, s->isdet, s->isgeneral, s->cfg.isrf, s->carveout, s->repack, st));
 
         if (part == 0) {     // the streams continue from the states the pilot wrote back (no reseeding)
             CUK(mmcb_k_hot_select(s->d_field, s->efieldlen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys,

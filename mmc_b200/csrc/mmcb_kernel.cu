@@ -1606,6 +1606,8 @@ mmcb_photon_kernel(const mmcb_kargs a) {
     }
 }
 
+#include "mmcb_kernel_rp.cuh"
+
 // elem -> node spreading for nodal output with the BLB tracer (the reference does this on the host,
 // src/mmc_cu_host.cu:929-975): node += 0.25 * elem for the 4 nodes of each element, per gate and pattern.
 __global__ void mmcb_spread_nodes_kernel(const acc_t* __restrict__ efield, double* __restrict__ nfield, const int* __restrict__ elem,
@@ -1857,9 +1859,24 @@ static photon_kernel_t pick_kernel(int method, int isdet, int isgeneral, int isr
     }
 }
 
+static photon_kernel_t pick_kernel_rp(int method, int isdet) {      // lane re-packing kernels (mmcb_kernel_rp.cuh)
+    if (method == 4) {
+        return isdet ? mmcb_photon_kernel_rp<4, true> : mmcb_photon_kernel_rp<4, false>;
+    }
+
+    return isdet ? mmcb_photon_kernel_rp<3, true> : mmcb_photon_kernel_rp<3, false>;
+}
+
+// shared memory the re-packing kernel needs on top of the media table (and hot-line cache): per warp 32 stashed walkers and the
+// slot-rank scratch, plus two partial-path columns per thread
+extern "C" size_t mmcb_k_rp_smem(int block, int isdet, int devreclen) {
+    const size_t nwarp = (size_t)block / 32;
+    return nwarp * ((isdet ? 7 : 5) * MMCB_RP_SLOTS * 16 + 32 * 4) + (isdet ? sizeof(float) * (size_t)devreclen * 2 * block : 0);
+}
+
 extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int carveout,
-                                     cudaStream_t st) {
-    photon_kernel_t k = pick_kernel(method, isdet, isgeneral, isrf);
+                                     int repack, cudaStream_t st) {
+    photon_kernel_t k = repack ? pick_kernel_rp(method, isdet) : pick_kernel(method, isdet, isgeneral, isrf);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 
     if (e != cudaSuccess) {
@@ -1880,12 +1897,12 @@ extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, s
     return (int)cudaGetLastError();
 }
 
-extern "C" int mmcb_k_max_block(int method) {      // largest (and default) block size the kernel of this tracer is compiled for
-    return (method <= 1) ? MMCB_MAXTHREADS_HP : MMCB_MAXTHREADS;
+extern "C" int mmcb_k_max_block(int method, int repack) {      // largest (and default) block size the kernel of this tracer is compiled for
+    return repack ? MMCB_RP_THREADS : ((method <= 1) ? MMCB_MAXTHREADS_HP : MMCB_MAXTHREADS);
 }
 
-extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int* blocks_per_sm) {
-    photon_kernel_t k = pick_kernel(method, isdet, isgeneral, isrf);
+extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int repack, int* blocks_per_sm) {
+    photon_kernel_t k = repack ? pick_kernel_rp(method, isdet) : pick_kernel(method, isdet, isgeneral, isrf);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 
     if (e == cudaSuccess) {

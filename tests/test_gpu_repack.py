@@ -1,0 +1,93 @@
+"""Parity of the experimental lane re-packing kernel (mmc_b200/csrc/mmcb_kernel_rp.cuh, opt-in with MMCB_REPACK=1) against the
+CPU oracle and against the flattened kernel.  The kernel is slower than the flattened one (profiles/r2a_repack_*) and is not the
+default; the tests keep it honest: walkers migrate between lanes through shared memory, so a lost or duplicated walker, a stream
+that leaves its photon or a deposit run that is dropped in an exchange would show here."""
+import numpy as np
+import pytest
+
+import cases
+import orc
+from test_gpu_parity import _cfg, _finite
+
+pytestmark = pytest.mark.gpu
+
+mmc = pytest.importorskip("mmc_b200")
+
+
+@pytest.fixture()
+def repack(monkeypatch):
+    monkeypatch.setenv("MMCB_REPACK", "1")
+
+
+@pytest.mark.parametrize("name", ["blb_elem_reflect", "grid_halfmm", "blb_onegate", "blb_detectors", "planar_widedet", "disk_grid"])
+def test_repack_statistical_parity_vs_oracle(name, repack):
+    node, elem, et, med = cases.case_mesh(name)
+    kw = cases.case_kwargs(name)
+    N = 200000
+    kw["nphoton"] = N
+    o = orc.run(node, elem, et, med, nthread=8, gpu_semantics=1, **kw)
+    g = mmc.run(_cfg(node, elem, et, med, **kw))
+    assert g["energytot"][0] == pytest.approx(o["launchweight"][0], abs=2e-3 * N)
+    fo = (o["launchweight"][0] - o["escweight"][0]) / o["launchweight"][0]
+    fg = g["energyabs"][0] / g["energytot"][0]
+    sigma = np.sqrt(max(fo * (1 - fo), 1e-4) / N)
+    assert abs(fg - fo) < 6 * sigma + 3e-4, (fg, fo, sigma)
+    assert abs(g["raytet"] / o["raytet"] - 1) < 0.02
+    fo_, fg_ = _finite(o["field"][..., 0]), _finite(g["raw"][..., 0])
+    go, gg = fo_.sum(axis=1), fg_.sum(axis=1)
+    big = go > 0.02 * fo_.sum()
+    np.testing.assert_allclose(gg[big], go[big], rtol=0.03)
+    cw_o, cw_g = fo_.sum(axis=0), fg_.sum(axis=0)
+    lit = cw_o > 0.02 * cw_o.max()
+    rel = np.abs(cw_g[lit] - cw_o[lit]) / cw_o[lit]
+    assert np.median(rel) < 0.05 and np.mean(rel) < 0.08, (np.median(rel), np.mean(rel))
+    if kw.get("issavedet"):
+        no, ng = o["detectedcount"], len(g["detp"])
+        assert abs(no - ng) < 6 * np.sqrt(max(no, 1)) + 5, (no, ng)
+
+
+def test_repack_energy_is_conserved(repack):
+    """sum(raw deposits) == launched - escaped: no pending run is lost when a walker moves between a lane and the stash."""
+    node, elem, et, med = cases.two_media_cube()
+    for name in ("blb_energy", "grid_halfmm"):
+        kw = cases.case_kwargs(name)
+        kw.update(nphoton=300000, isnormalized=0, outputtype=cases.ENERGY)
+        g = mmc.run(_cfg(node, elem, et, med, **kw))
+        assert abs(g["raw"].sum() / g["energyabs"][0] - 1) < 2e-4, name
+
+
+def test_repack_walker_keeps_its_stream(repack):
+    """A detected photon's saved launch seed, replayed by the oracle, must give the same record: the xorshift128+ stream travels
+    with the walker through every exchange (src/mmc_core.cl:2191-2194 is the replay contract)."""
+    node, elem, et, med = cases.two_media_cube()
+    kw = cases.case_kwargs("blb_detectors")
+    kw.update(nphoton=20000, issaveseed=1)
+    g = mmc.run(_cfg(node, elem, et, med, **kw))
+    n = len(g["detp"])
+    assert n > 300
+    seeds = np.ascontiguousarray(g["seeds"]).view(np.uint64).reshape(n, 2)
+    o = orc.run(node, elem, et, med, nthread=4, gpu_semantics=1, seed=orc.SEED_FROM_FILE, photonseed=seeds,
+                replayweight=np.ones(n, np.float32), replaytime=np.zeros(n, np.float32),
+                **{k: v for k, v in kw.items() if k not in ("seed", "nphoton")}, nphoton=n)
+    key_o = {tuple(s): i for i, s in enumerate(o["detseed"])}
+    both = [(key_o[tuple(s)], j) for j, s in enumerate(g["seeds"]) if tuple(s) in key_o]
+    assert len(both) > 0.97 * n, (len(both), n)
+    io, ig = np.array(both).T
+    do, dg = o["detected"][io], g["detp"][ig]
+    same = np.all(np.abs(do - dg) <= 2e-3 * np.maximum(1.0, np.abs(do)), axis=1)
+    assert same.mean() > 0.9, same.mean()
+
+
+def test_repack_agrees_with_flattened_kernel(monkeypatch):
+    node, elem, et, med = cases.two_media_cube()
+    kw = cases.case_kwargs("grid_1mm")
+    kw["nphoton"] = 400000
+    monkeypatch.delenv("MMCB_REPACK", raising=False)
+    a = mmc.run(_cfg(node, elem, et, med, **kw))
+    monkeypatch.setenv("MMCB_REPACK", "1")
+    b = mmc.run(_cfg(node, elem, et, med, **kw))
+    assert a["energytot"][0] == b["energytot"][0] == kw["nphoton"]
+    assert abs(a["energyabs"][0] / b["energyabs"][0] - 1) < 5e-3
+    assert abs(a["raytet"] / b["raytet"] - 1) < 5e-3
+    ga, gb = _finite(a["raw"][..., 0]).sum(axis=1), _finite(b["raw"][..., 0]).sum(axis=1)
+    np.testing.assert_allclose(ga[:6], gb[:6], rtol=0.02)
