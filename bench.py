@@ -117,6 +117,63 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def l2_peaks(ne, nvol, device=0):
+    """The two ceilings SURVEY.md section 8(d) names, measured on THIS GPU right before the timed region with tools/microbench
+    (MEASURED_PEAKS.json holds neither): dependent random 96-byte record gathers (three 256-bit loads, the photon kernel's access)
+    from a table of the mesh's size, and random fire-and-forget f64 reductions into a volume of the accumulator's size.  The run
+    takes about half a second.  Falls back to the round-1 figures (profiles/r1_microbench_l2gather_atomics.jsonl) when the binary
+    is missing."""
+    mb = os.path.join(ROOT, "tools", "microbench")
+    out = {"gather_gsteps": 150.0, "red_gatomics": 196.0, "source": "fallback: profiles/r1_microbench_l2gather_atomics.jsonl (B200, round 1)"}
+    if os.path.exists(mb):
+        try:
+            r = subprocess.run([mb, "quick", str(int(ne)), str(int(max(nvol, 1024))), str(device)], capture_output=True, text=True, timeout=120)
+            for line in r.stdout.splitlines():
+                j = json.loads(line)
+                if j.get("bench") == "gather":
+                    out["gather_gsteps"] = j["Gsteps_s"]
+                elif j.get("bench") == "red":
+                    out["red_gatomics"] = j["Gatomics_s"]
+            out["source"] = "tools/microbench quick %d %d, run inside bench.py before the timed region" % (ne, nvol)
+        except Exception as e:      # noqa: BLE001
+            out["source"] += " (live run failed: %s)" % str(e)[:80]
+    return out
+
+
+def ref_cuda_run(cfg, nphoton):
+    """The reference's own CUDA kernel (oracle/_ref/mmc_refcuda: the unmodified src/mmc_cu_host.cu + mmc_core.cl compiled for sm_100 by
+    oracle/Makefile.ref) on the same workload and photon count, on this GPU.  Time = its own `kernel complete: N ms` line (host clock
+    around launch + synchronise, whole milliseconds, src/mmc_cu_host.cu:640,748-753)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    from mmc_b200 import api
+    if not orc.ref_available(cuda=True):
+        return {"unavailable": "oracle/_ref/mmc_refcuda was not built (needs /root/reference at build time)"}
+    st = cfg.get("srctype", 0)
+    kw = dict(nphoton=int(nphoton), seed=cfg["seed"], srcpos=cfg["srcpos"], srcdir=cfg["srcdir"],
+              srctype=api.SRCTYPES.index(st) if isinstance(st, str) else st,
+              srcparam1=cfg.get("srcparam1", (0, 0, 0, 0)), srcparam2=cfg.get("srcparam2", (0, 0, 0, 0)),
+              tstart=cfg["tstart"], tend=cfg["tend"], tstep=cfg["tstep"], e0=cfg.get("e0", 0), isreflect=cfg["isreflect"],
+              method=api.METHODS[cfg["method"]], basisorder=0, steps=cfg.get("steps", (1.0,))[0], evol=cfg.get("evol"),
+              issavedet=cfg.get("issavedet", 0), detpos=cfg.get("detpos"), maxdetphoton=cfg.get("maxdetphoton", 1000000))
+    try:
+        runs = []
+        for _ in range(2):          # the first run of the process pays context creation outside the kernel line; keep the faster kernel time
+            r = orc.run_ref(np.asarray(cfg["node"], np.float32), np.asarray(cfg["elem"], np.int32), np.asarray(cfg["elemprop"], np.int32),
+                            np.asarray(cfg["prop"], np.float32)[1:], cuda=True, timeout=900, **kw)
+            if r.get("kernel_ms"):
+                runs.append(r)
+        if not runs:
+            return {"unavailable": "no `kernel complete` line in the reference's output"}
+        best = min(runs, key=lambda q: q["kernel_ms"])
+        return {"value": nphoton / best["kernel_ms"], "unit": "photons/ms", "kernel_ms": best["kernel_ms"], "photons": int(nphoton),
+                "absorbed_fraction": best.get("absorbed_frac"), "runs_ms": [q["kernel_ms"] for q in runs],
+                "what": "unmodified reference CUDA kernel (src/mmc_core.cl via src/mmc_cu_host.cu, -gencode arch=compute_100,code=sm_100), same mesh / optics / "
+                        "photon count on this GPU, its own `kernel complete` time"}
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": str(e)[-300:]}
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # the reference arm / CPU baseline
 # --------------------------------------------------------------------------------------------------------------------
@@ -183,6 +240,7 @@ def main():
     ap.add_argument("--ref-photons", type=float, default=1e6)      # ~6 s of CPU work per sample at 16 host threads (the reference CPU path runs this workload at 0.15-0.27 k photons/ms)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
     args = ap.parse_args()
     cfg, desc = workload(args.workload, args.method)
     nphoton = int(args.photons)
@@ -218,6 +276,7 @@ def main():
     field = torch.zeros(dp.fieldlen, dtype=torch.float64 if dp.field_is_double else torch.float32, device=dev)
     sess.set_field_buffer(field.data_ptr())
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    l2pk = l2_peaks(len(cfg["elem"]), dp.fieldlen, local) if rank == 0 else None
 
     # everything of a step (L2 flush, photon kernel, NCCL reduce, timing events) is enqueued on ONE explicit non-default
     # stream: torch.cuda.Event only sees the stream it is recorded on, and a NULL stream handle would make the C-ABI fall
@@ -237,7 +296,11 @@ def main():
             # stream makes each rank generate and discard the other ranks' words (17 ms per step at 8 ranks)
             sess.launch(nphoton, photon_offset=0, seed=cfg["seed"] + 7919 * rank, seed_offset=i, stream=stream.cuda_stream)
             if dist is not None:
+                # every step reduces what THIS step deposited: the ranks' volumes are summed into rank 0's and zeroed on the others, so
+                # nothing is added twice and rank 0 ends with the sum over all ranks and steps
                 dist.reduce(field, dst=0, op=dist.ReduceOp.SUM)
+                if rank != 0:
+                    field.zero_()
             e1.record(stream)
             stream.synchronize()
         return e0.elapsed_time(e1), sess.sync()
@@ -310,26 +373,54 @@ def main():
     steps_per_launch = raytet / args.steps
     kernel_ms = total_kern_ms / args.steps
     achieved = steps_per_launch * bps / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # dram__bytes_read+write per launch from the last `ncu --set full` capture
+    # from the last `ncu --set full` capture of this workload (profiles/ncu_traffic.json): DRAM bytes, global reductions and issue-slot
+    # utilisation per launch
+    ncu = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
-        t = json.load(open(tpath)).get("%s:%s" % (args.workload, cfg["method"]))
-        traffic = t["dram_bytes_per_launch"] if t else None
+        ncu = json.load(open(tpath)).get("%s:%s" % (args.workload, cfg["method"])) or {}
+    traffic = ncu.get("dram_bytes_per_launch")
+    gsteps = steps_per_launch / (kernel_ms * 1e-3) / 1e9
+    # the mesh tables (and here the volume) are L2-resident, so the memory-system ceiling is the L2 GATHER rate
+    # (one 96-byte record per ray-tet step), next to it the L2 ATOMIC rate for the deposits; HBM is the ceiling only for volumes that
+    # spill.  All three are reported; `bound` names the one with the largest fraction, in the algorithmic bytes of section 8(d)
+    # (92 B per step) so that achieved / peak is the ratio of step rates.
+    fr_gather = gsteps / l2pk["gather_gsteps"]
+    reds = ncu.get("global_reds_per_photon")
+    gred = (reds * nphoton / (kernel_ms * 1e-3) / 1e9) if reds else None
+    fr_atomic = (gred / l2pk["red_gatomics"]) if gred else None
+    fr_hbm = achieved / hbm
+    cands = [("l2_gather", fr_gather, l2pk["gather_gsteps"] * bps)] + ([("atomic", fr_atomic, None)] if fr_atomic else []) + [("hbm", fr_hbm, hbm)]
+    bound = max(cands, key=lambda c: c[1])[0]
+    roof = {"bound": bound, "unit": "GB/s", "traffic": traffic, "kernel_ms": kernel_ms, "gsteps_per_s": gsteps,
+            "l2_gather": {"achieved_gsteps_per_s": gsteps, "peak_gsteps_per_s": l2pk["gather_gsteps"], "frac": fr_gather},
+            "atomic": {"achieved_gred_per_s": gred, "peak_gred_per_s": l2pk["red_gatomics"], "frac": fr_atomic,
+                       "reds_per_photon": reds, "reds_source": ncu.get("report")},
+            "hbm_equivalent": {"achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": fr_hbm, "peak_source": peak_src},
+            "issue": {"issue_slots_busy": ncu.get("issue_slots_busy"), "ipc": ncu.get("ipc"), "active_threads_per_warp_inst": ncu.get("active_threads"),
+                      "source": ncu.get("report")},
+            "peak_source": l2pk["source"],
+            "note": "algorithmic bytes = %d B per ray-tet step (84 B record gather + 8 B atomic payload) x %.3g steps per launch; achieved and peak of the "
+                    "named bound are both in those bytes.  DRAM traffic per launch (`traffic`) is a few MB: nothing here is HBM-bound.  The unit that "
+                    "actually limits the kernel is instruction issue (`issue`, from ncu)." % (bps, steps_per_launch)}
+    if bound == "atomic":
+        roof.update(achieved=gred * 8, peak=l2pk["red_gatomics"] * 8, frac=fr_atomic)
+    elif bound == "hbm":
+        roof.update(achieved=achieved, peak=hbm, frac=fr_hbm)
+    else:
+        roof.update(achieved=achieved, peak=l2pk["gather_gsteps"] * bps, frac=fr_gather)
     line = {"metric": "photons/ms", "value": value, "unit": "photons/ms", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "photons_per_step_per_gpu": nphoton, "l2": "flushed between timed steps (192 MiB fill)",
                        "accumulator": "f64 red.global.add" if dp.field_is_double else "f32 red.global.add",
-                       "raytet_steps_per_photon": steps_per_launch / nphoton, "absorbed_fraction": absorbed},
+                       "raytet_steps_per_photon": steps_per_launch / nphoton, "absorbed_fraction": absorbed,
+                       "e2e_warmup_calls": 1, "reference_arm_photons_per_step": int(args.ref_photons),
+                       "reference_arm_note": "the CPU arm runs %d photons per step of the same mesh / optics (a rate metric; %d photons would take "
+                                             "about a minute per step on the host cores)" % (int(args.ref_photons), nphoton)},
             "gpu_launches": args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms,
-                         "gsteps_per_s": steps_per_launch / (kernel_ms * 1e-3) / 1e9,
-                         "note": "algorithmic bytes = %d B per ray-tet step x %.3g steps per launch.  Mesh tables and volume are L2-resident (DRAM traffic "
-                                 "per launch is the `traffic` field), so the kernel is not HBM-bound: ncu at 1e7 photons shows 84%% issue slots busy, IPC 3.33 (sphshells grid; 72%% cube60 elem): "
-                                 "instruction-issue bound (profiles/r1k_ncu_*); measured L2 ceilings on this box: 130-150 G record gathers/s, 196 G red/s, 0.7 G red/s on one 128 B line "
-                                 "(profiles/r1_microbench_l2gather_atomics.jsonl)" % (bps, steps_per_launch)}}
+            "roofline": roof}
     if e2e is not None:
         line["e2e"] = e2e
 
@@ -338,6 +429,10 @@ def main():
         c = cpu_reference_run(cfg, int(args.ref_photons), threads)
         line["cpu_baseline"] = {"value": c["value"], "unit": "photons/ms", "cores": threads, "kind": c["kind"],
                                 "sample": "%d photons of the same workload, one run, reference CPU path with all host threads" % int(args.ref_photons)}
+    if not args.no_ref_cuda and world == 1:          # the competitor north_star names: the reference's own CUDA kernel on this GPU
+        rc = ref_cuda_run(cfg, nphoton)
+        line["ref_cuda"] = rc
+        line["vs_ref_cuda"] = (value / rc["value"]) if rc.get("value") else None
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

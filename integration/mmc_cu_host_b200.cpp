@@ -131,6 +131,32 @@ extern "C" void mmc_run_cu(mcconfig* cfg, tetmesh* mesh, raytracer* tracer) {
         }
     }
 
+    // The callers have already consumed two things the C-ABI takes in their original form:
+    //  * labels: mesh_srcdetelem (src/mmc_mesh.c:390-427) moved the -1 labels (wide-field source candidates) into mesh->srcelem and
+    //    reset them to 0; mesh_loadmedia / mesh_validate turned the -2 labels (wide-field detector) into prop+1.  The engine builds its
+    //    candidate list and its detector medium from -1 / -2, so they are restored on a copy.
+    //  * media: mua and mus were multiplied by cfg->unitinmm (src/mmc_mesh.c:542-546, :2396-2399); the engine applies the length unit
+    //    itself (mmcb_config.unitinmm), so the copy divides it out again.
+    std::vector<int> type(mesh->type, mesh->type + mesh->ne);
+
+    for (int i = 0; i < mesh->srcelemlen; i++) {
+        type[mesh->srcelem[i] - 1] = -1;
+    }
+
+    for (int i = 0; i < mesh->detelemlen; i++) {
+        type[mesh->detelem[i] - 1] = -2;
+    }
+
+    std::vector<mmcb_medium> med(mesh->prop + 1);
+    const float unit = (cfg->unitinmm > 0.f) ? cfg->unitinmm : 1.f;
+
+    for (int i = 0; i <= mesh->prop; i++) {
+        med[i].mua = mesh->med[i].mua / (i ? unit : 1.f);
+        med[i].mus = mesh->med[i].mus / (i ? unit : 1.f);
+        med[i].g = mesh->med[i].g;
+        med[i].n = mesh->med[i].n;
+    }
+
     mmcb_mesh m;
     memset(&m, 0, sizeof(m));
     m.nn = mesh->nn;
@@ -138,8 +164,8 @@ extern "C" void mmc_run_cu(mcconfig* cfg, tetmesh* mesh, raytracer* tracer) {
     m.prop = mesh->prop;
     m.node = node.data();
     m.elem = elem.data();
-    m.type = mesh->type;
-    m.med = (const mmcb_medium*)mesh->med;
+    m.type = type.data();
+    m.med = med.data();
     m.facenb = facenb.empty() ? NULL : facenb.data();
     m.evol = mesh->evol;
     m.nvol = NULL;              // mesh->nvol already carries the surface correction of tracer_prep; the engine recomputes both
@@ -301,6 +327,10 @@ extern "C" void mmc_run_cu(mcconfig* cfg, tetmesh* mesh, raytracer* tracer) {
     cfg->detectedcount = out.detectedcount;
     cfg->his.detected = out.detectedtotal;
     cfg->debugdatalen = out.trajcount;
+
+    if (cfg->issavedet && out.detectedtotal > 0) {      // src/mmc_cu_host.cu:828
+        MMC_FPRINTF(cfg->flog, "detected %d photons, total: %d\t", (int)out.detectedcount, (int)out.detectedtotal);
+    }
 
     if (out.detectedtotal > cfg->maxdetphoton) {
         MMC_FPRINTF(cfg->flog, S_RED "WARNING: the detected photon (%d) is more than what your have specified (%d), please use the -H option to specify a greater number\t" S_RESET,

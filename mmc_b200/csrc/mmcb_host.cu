@@ -33,7 +33,8 @@ extern "C" int mmcb_k_build_records(const float* d_node, const int* d_elem, cons
 // mesh_normalize on the device (mmcb_post.cu)
 extern "C" int mmcb_k_norm_sum(const double* W, size_t nentry, int srcnum, double* dep, cudaStream_t st);
 extern "C" int mmcb_k_norm_nvol(double* W, size_t n, int nn, int srcnum, const float* nvol, cudaStream_t st);
-extern "C" int mmcb_k_norm_elemdep(const double* W, const int* elem, const float* evol, const float* emua, int ne, int nn, int maxgate, int srcnum,
+extern "C" int mmcb_k_double_to_float(const double* in, float* out, size_t n, cudaStream_t st);
+extern "C" int mmcb_k_norm_elemdep(const double* W, const double* Wim, const int* elem, const float* evol, const float* emua, int ne, int nn, int maxgate, int srcnum,
                                    double* dep, cudaStream_t st);
 extern "C" int mmcb_k_norm_scale(const double* in, double* out, size_t n, int datalen, int srcnum, const float* evol, const float* emua,
                                  const double* fac16, cudaStream_t st);
@@ -189,34 +190,43 @@ struct PrepMesh {
     float nmin[3], nmax[3];
 };
 
+// ---- element volumes.  The arithmetic of the determinant is the reference's (src/mmc_mesh.c:916-925: the volumes are inputs of the
+// normalisation and are compared bit for bit with the reference's tables); everything around it is written for this engine: one pass
+// that measures and orients the elements, one pass that hands a quarter of each volume to its nodes.
+inline float tet_volume6(const float* a, const float* b, const float* c, const float* d) {
+    const float ex = c[0] - d[0], ey = c[1] - d[1], ez = c[2] - d[2];
+    const float yz = c[1] * d[2] - c[2] * d[1], xz = c[0] * d[2] - c[2] * d[0], xy = c[0] * d[1] - c[1] * d[0];
+    float v = b[0] * yz - b[1] * xz + b[2] * xy;
+    v += -a[0] * (yz + b[1] * ez - b[2] * ey);
+    v += +a[1] * (xz + b[0] * ez - b[2] * ex);
+    v += -a[2] * (xy + b[0] * ey - b[1] * ex);
+    return -v;
+}
+
 void volumes(int nn, const float* node, int ne, int* elem, const int* type, float* evol, float* nvol) {
-    // mesh_getvolume, src/mmc_mesh.c:910-948
-    std::fill(nvol, nvol + nn, 0.f);
+    for (int e = 0; e < ne; e++) {          // inverted elements get their last two nodes swapped (mesh_getvolume does the same in place)
+        int* q = elem + 4 * (size_t)e;
+        float v6 = tet_volume6(nd(node, q[0]), nd(node, q[1]), nd(node, q[2]), nd(node, q[3]));
 
-    for (int i = 0; i < ne; i++) {
-        int* ee = elem + 4 * (size_t)i;
-        const float* n0 = nd(node, ee[0]), *n1 = nd(node, ee[1]), *n2 = nd(node, ee[2]), *n3 = nd(node, ee[3]);
-        float dx = n2[0] - n3[0], dy = n2[1] - n3[1], dz = n2[2] - n3[2];
-        float v = n1[0] * (n2[1] * n3[2] - n2[2] * n3[1]) - n1[1] * (n2[0] * n3[2] - n2[2] * n3[0]) + n1[2] * (n2[0] * n3[1] - n2[1] * n3[0]);
-        v += -n0[0] * ((n2[1] * n3[2] - n2[2] * n3[1]) + n1[1] * dz - n1[2] * dy);
-        v += +n0[1] * ((n2[0] * n3[2] - n2[2] * n3[0]) + n1[0] * dz - n1[2] * dx);
-        v += -n0[2] * ((n2[0] * n3[1] - n2[1] * n3[0]) + n1[0] * dy - n1[1] * dx);
-        v = -v;
-
-        if (v < 0.f) {
-            std::swap(ee[2], ee[3]);
-            v = -v;
+        if (v6 < 0.f) {
+            std::swap(q[2], q[3]);
+            v6 = -v6;
         }
 
-        v *= (1.f / 6.f);
-        evol[i] = v;
+        evol[e] = v6 * (1.f / 6.f);
+    }
 
-        if (type && type[i] == 0) {
+    std::fill(nvol, nvol + nn, 0.f);
+
+    for (int e = 0; e < ne; e++) {          // void elements (label 0) carry no nodal volume
+        if (type && type[e] == 0) {
             continue;
         }
 
-        for (int j = 0; j < 4; j++) {
-            nvol[ee[j] - 1] += v * 0.25f;
+        const float quarter = evol[e] * 0.25f;
+
+        for (int k = 0; k < 4; k++) {
+            nvol[elem[4 * (size_t)e + k] - 1] += quarter;
         }
     }
 }
@@ -264,90 +274,93 @@ void facenb_build(int ne, const int* elem, int* facenb) {
     }
 }
 
+// ---- point location.  inside_weights: un-normalised barycentric weights of `pt` in element `e` from the four face planes, weight of
+// local node FACEMAP[f] = -(pt - A_f) . ((B_f - A_f) x (C_f - A_f)) with the face nodes in the reference's order (src/mmc_mesh.c:59,1180-1190:
+// the enclosing element must come out the same for sources that sit on a face).  Returns false when the point is outside.
+bool inside_weights(const float* node, const int* quad, const float* pt, float w[4]) {
+    bool inside = true;
+
+    for (int f = 0; f < 4; f++) {
+        const float* A = nd(node, quad[OUT[f][0]]), *B = nd(node, quad[OUT[f][1]]), *C = nd(node, quad[OUT[f][2]]);
+        const float u[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, v[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
+        const float r[3] = {pt[0] - A[0], pt[1] - A[1], pt[2] - A[2]};
+        const float n[3] = {u[1]* v[2] - u[2]* v[1], u[2]* v[0] - u[0]* v[2], u[0]* v[1] - u[1]* v[0]};
+        w[FACEMAP[f]] = -(r[0] * n[0] + r[1] * n[1] + r[2] * n[2]);
+    }
+
+    for (int k = 0; k < 4; k++) {
+        inside = inside && !(w[k] < 0.f);
+    }
+
+    return inside;
+}
+
+// barycentric coordinates of srcpos in element e0 (1-based); non-zero when e0 is invalid or does not enclose the point (mesh_barycentric)
 int barycentric(const float* node, const int* elem, int ne, int e0, float* bary, const float* srcpos) {
-    // mesh_barycentric, src/mmc_mesh.c:1170-1206
-    if (e0 < 1 || e0 > ne) {
+    if (e0 < 1 || e0 > ne || !inside_weights(node, elem + 4 * (size_t)(e0 - 1), srcpos, bary)) {
         return 1;
     }
 
-    const int* ee = elem + 4 * (size_t)(e0 - 1);
-    float s = 0.f;
+    float total = 0.f;
 
-    for (int i = 0; i < 4; i++) {
-        const float* a = nd(node, ee[OUT[i][0]]), *b = nd(node, ee[OUT[i][1]]), *c = nd(node, ee[OUT[i][2]]);
-        float AB[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, AC[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
-        float S[3] = {srcpos[0] - a[0], srcpos[1] - a[1], srcpos[2] - a[2]};
-        float N[3] = {AB[1]* AC[2] - AB[2]* AC[1], AB[2]* AC[0] - AB[0]* AC[2], AB[0]* AC[1] - AB[1]* AC[0]};
-        bary[FACEMAP[i]] = -(S[0] * N[0] + S[1] * N[1] + S[2] * N[2]);
+    for (int k = 0; k < 4; k++) {
+        total += bary[k];
     }
 
-    for (int i = 0; i < 4; i++) {
-        if (bary[i] < 0.f) {
-            return 1;
-        }
-
-        s += bary[i];
-    }
-
-    for (int i = 0; i < 4; i++) {
-        bary[i] /= s;
+    for (int k = 0; k < 4; k++) {
+        bary[k] /= total;
     }
 
     return 0;
 }
 
+// first element (lowest index, like mesh_initelem's scan) whose bounding box and four planes enclose srcpos; 0 when there is none
 int initelem(const float* node, const int* elem, int ne, const float* srcpos, float* bary) {
-    // mesh_initelem, src/mmc_mesh.c:1060-1090
-    for (int i = 0; i < ne; i++) {
-        double pmin[3] = {VERY_BIG, VERY_BIG, VERY_BIG}, pmax[3] = { -VERY_BIG, -VERY_BIG, -VERY_BIG};
-        const int* ee = elem + 4 * (size_t)i;
+    for (int e = 0; e < ne; e++) {
+        const int* q = elem + 4 * (size_t)e;
+        bool inbox = true;
 
-        for (int j = 0; j < 4; j++) {
-            const float* p = nd(node, ee[j]);
-
-            for (int k = 0; k < 3; k++) {
-                pmin[k] = std::min(pmin[k], (double)p[k]);
-                pmax[k] = std::max(pmax[k], (double)p[k]);
-            }
+        for (int k = 0; k < 3 && inbox; k++) {
+            const float c0 = nd(node, q[0])[k], c1 = nd(node, q[1])[k], c2 = nd(node, q[2])[k], c3 = nd(node, q[3])[k];
+            const float lo = std::min(std::min(c0, c1), std::min(c2, c3)), hi = std::max(std::max(c0, c1), std::max(c2, c3));
+            inbox = (srcpos[k] >= lo && srcpos[k] <= hi);
         }
 
-        if (srcpos[0] <= pmax[0] && srcpos[0] >= pmin[0] && srcpos[1] <= pmax[1] && srcpos[1] >= pmin[1] &&
-                srcpos[2] <= pmax[2] && srcpos[2] >= pmin[2]) {
-            if (barycentric(node, elem, ne, i + 1, bary, srcpos) == 0) {
-                return i + 1;
-            }
+        if (inbox && barycentric(node, elem, ne, e + 1, bary, srcpos) == 0) {
+            return e + 1;
         }
     }
 
     return 0;
 }
 
+// Effective reflection coefficient of a diffusing medium against the outside (the nodal-volume correction of surface nodes,
+// src/mmc_mesh.c:1344-1386): the Fresnel reflectance of unpolarised light, R(t), weighted over the half space,
+//     R_phi = int 2 sin t cos t R dt,   R_j = int 3 sin t cos^2 t R dt,   Reff = (R_phi + R_j) / (2 - R_phi + R_j),
+// by the rectangle rule on 1000 angles, which is what mesh_getreff (:2305-2334) integrates with -- the same nodes and weights, so
+// the corrected volumes agree with the reference's.
 double getreff(double n_in, double n_out) {
-    // mesh_getreff, src/mmc_mesh.c:2305-2334
-    double oc = asin(1.0 / n_in);
-    const double count = 1000.0, ostep = (M_PI / (2.0 * count));
+    const int nangle = 1000;
+    const double dt = M_PI / (2.0 * nangle), critical = asin(1.0 / n_in);
+    auto fresnel = [&](double t) {
+        if (!(t < critical)) {
+            return 1.0;
+        }
+
+        const double ci = cos(t), si = n_in * sin(t), ct = sqrt(1. - si * si);
+        const double rs = (n_in * ct - n_out * ci) / (n_in * ct + n_out * ci), rp = (n_in * ci - n_out * ct) / (n_in * ci + n_out * ct);
+        return 0.5 * rs * rs + 0.5 * rp * rp;
+    };
     double r_phi = 0.0, r_j = 0.0;
 
-    for (int i = 0; i < count; i++) {
-        double o = i * ostep, coso = cos(o), r_fres;
-
-        if (o < oc) {
-            double cosop = n_in * sin(o);
-            cosop = sqrt(1. - cosop * cosop);
-            double tmp = (n_in * cosop - n_out * coso) / (n_in * cosop + n_out * coso);
-            r_fres = 0.5 * tmp * tmp;
-            tmp = (n_in * coso - n_out * cosop) / (n_in * coso + n_out * cosop);
-            r_fres += 0.5 * tmp * tmp;
-        } else {
-            r_fres = 1.f;
-        }
-
-        r_phi += 2.0 * sin(o) * coso * r_fres;
-        r_j += 3.0 * sin(o) * coso * coso * r_fres;
+    for (int k = 0; k < nangle; k++) {
+        const double t = k * dt, R = fresnel(t);
+        r_phi += 2.0 * sin(t) * cos(t) * R;
+        r_j += 3.0 * sin(t) * cos(t) * cos(t) * R;
     }
 
-    r_phi *= ostep;
-    r_j *= ostep;
+    r_phi *= dt;
+    r_j *= dt;
     return (r_phi + r_j) / (2.0 - r_phi + r_j);
 }
 
@@ -491,6 +504,14 @@ int validate(const mmcb_config* in, const mmcb_mesh* mesh, Cfg& o) {
     }
 
     const bool isadjoint = (c.outputtype >= MMCB_OT_ADJOINT);
+
+    if ((c.outputtype == MMCB_OT_JACOBIAN || c.outputtype == MMCB_OT_WL || c.outputtype == MMCB_OT_WP) && c.seed != MMCB_SEED_FROM_FILE) {
+        return fail(MMCB_ERR_INPUT, "Jacobian output is only valid in the reply mode. Please give an mch file after '-E'.");    // src/mmc_utils.c:4266-4268
+    }
+
+    if (isadjoint && c.seed == MMCB_SEED_FROM_FILE) {
+        return fail(MMCB_ERR_INPUT, "Adjoint Jacobian output is not valid in replay mode.");       // src/mmc_utils.c:4270-4272
+    }
 
     if (c.extrasrclen < 0 || (c.extrasrclen > 0 && !c.srcdata)) {
         return fail(MMCB_ERR_INPUT, "extrasrclen > 0 needs srcdata");
@@ -1661,8 +1682,8 @@ int mmcb_set_field_buffer(mmcb_session* s, void* device_ptr) {
 
     CU(cudaSetDevice(s->device));
 
-    if (!s->field_external) {
-        dev_free(s->d_field);
+    if (!s->field_external && s->d_field) {      // on the session's own stream: the thread-local default may belong to another session
+        CU(cudaFreeAsync(s->d_field, s->stream));
     }
 
     s->d_field = device_ptr;
@@ -1912,118 +1933,6 @@ static int rc_dev_alloc_float(float** d, const std::vector<float>& h, cudaStream
     return 0;
 }
 
-// mesh_normalize, src/mmc_mesh.c:2154-2279, on the host copy of the volume
-static double normalize_field(const mmcb_session* s, double* W, double* Wim, double* dref, float Eabsorb, float Etotal, int pair) {
-    // Wim: RF imaginary volume of this source slot (mesh_normalize's imag_slot, src/mmc_mesh.c:2204-2206) or NULL
-    const mmcb_config& c = s->cfg.c;
-    const PrepMesh& m = s->mesh;
-    const int datalen = s->cfg.datalen, maxgate = s->cfg.maxgate, srcnum = c.srcnum;
-    double energydeposit = 0.f, energyelem, normalizor;
-
-    if (c.issaveref && dref) {
-        float nz = 1.f / Etotal;
-
-        for (size_t i = 0; i < (size_t)maxgate * m.nf; i++) {
-            dref[i] *= nz;
-        }
-    }
-
-    if (c.seed == MMCB_SEED_FROM_FILE && (c.outputtype == MMCB_OT_JACOBIAN || c.outputtype == MMCB_OT_WL || c.outputtype == MMCB_OT_WP)) {
-        float nz = 1.f / (1e-4f * c.nphoton);
-
-        if (c.outputtype == MMCB_OT_WL || c.outputtype == MMCB_OT_WP) {
-            nz = 1.f / Etotal;
-        }
-
-        for (int i = 0; i < maxgate; i++)
-            for (int j = 0; j < datalen; j++) {
-                W[((size_t)i * datalen + j)*srcnum + pair] *= nz;
-            }
-
-        return nz;
-    }
-
-    if (c.outputtype == MMCB_OT_ENERGY) {
-        normalizor = 1.f / Etotal;
-
-        for (int i = 0; i < maxgate; i++)
-            for (int j = 0; j < datalen; j++) {
-                W[((size_t)i * datalen + j)*srcnum + pair] *= normalizor;
-            }
-
-        return normalizor;
-    }
-
-    if (c.method == MMCB_RT_BLBADOUEL_GRID) {
-        normalizor = 1.0 / (Etotal * c.unitinmm * c.unitinmm * c.unitinmm);
-    } else if (c.basisorder) {
-        for (int i = 0; i < maxgate; i++)
-            for (int j = 0; j < datalen; j++)
-                if (m.nvol[j] > 0.f) {
-                    W[((size_t)i * datalen + j)*srcnum + pair] /= m.nvol[j];
-
-                    if (Wim) {
-                        Wim[(size_t)i * datalen + j] /= m.nvol[j];
-                    }
-                }
-
-        for (int i = 0; i < m.ne; i++) {
-            const int* ee = &m.elem[4 * (size_t)i];
-            energyelem = 0.f;
-
-            for (int j = 0; j < maxgate; j++)
-                for (int k = 0; k < 4; k++) {
-                    float re_val = W[((size_t)j * m.nn + ee[k] - 1) * srcnum + pair];
-
-                    if (Wim) {          // RF: |phi| (:2232-2237)
-                        float im_val = Wim[(size_t)j * m.nn + ee[k] - 1];
-                        energyelem += sqrtf(re_val * re_val + im_val * im_val);
-                    } else {
-                        energyelem += re_val;
-                    }
-                }
-
-            energydeposit += energyelem * m.evol[i] * m.med[m.type[i]].mua;
-        }
-
-        normalizor = Eabsorb / (Etotal * energydeposit * 0.25f);
-    } else {
-        for (int i = 0; i < datalen; i++)
-            for (int j = 0; j < maxgate; j++) {
-                energydeposit += W[((size_t)j * datalen + i) * srcnum + pair];
-            }
-
-        for (int i = 0; i < datalen; i++) {
-            energyelem = m.evol[i] * m.med[m.type[i]].mua;
-
-            for (int j = 0; j < maxgate; j++) {
-                W[((size_t)j * datalen + i) * srcnum + pair] /= energyelem;
-
-                if (Wim) {      // the reference leaves the imaginary part undivided here (:2250-2256), which cannot be intended:
-                    Wim[(size_t)j * datalen + i] /= energyelem;     // both parts of one complex fluence get the same factor
-                }
-            }
-        }
-
-        normalizor = Eabsorb / (Etotal * energydeposit);
-    }
-
-    if (c.outputtype == MMCB_OT_FLUX) {
-        normalizor /= c.tstep;
-    }
-
-    for (int i = 0; i < maxgate; i++)
-        for (int j = 0; j < datalen; j++) {
-            W[((size_t)i * datalen + j)*srcnum + pair] *= normalizor;
-
-            if (Wim) {
-                Wim[(size_t)i * datalen + j] *= (float)normalizor;
-            }
-        }
-
-    return normalizor;
-}
-
 int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc, mmcb_output* out) {
     if (!s || !out) {
         return fail(MMCB_ERR_INPUT, "null argument");
@@ -2084,36 +1993,53 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
                 st[MMCB_HOT_STAT_USEFUL], st[1], tot > 0.f ? mx / tot : 0.f);
     }
 
-    // ---- common case (one slot, no RF): mesh_normalize runs on the device and the volume crosses PCIe once, in its final form
-    if (out->field && !s->cfg.isrf && s->cfg.nslots == 1 && !getenv("MMCB_HOST_NORM")) {
-        const bool nodal = (!s->isgrid && !s->ishp && c.basisorder);
-        const size_t n = s->fieldlen;
-        const int datalen = s->cfg.datalen, maxgate = s->cfg.maxgate, srcnum = c.srcnum;
-        double* d_out = NULL;
-        const double* d_src = (const double*)s->d_field;
+    // ---- the volume: elem -> node spreading, mesh_normalize (src/mmc_mesh.c:2154-2279) and the slot broadcast of the normaliser
+    //      (src/mmc_cu_host.cu:997-1060) all run on the device (mmcb_post.cu: mmcb_norm_*); the volume crosses PCIe once, in its final
+    //      form.  Layout: patterns interleaved [(gate*datalen + i)*srcnum + p]; multi-slot runs (srcnum == 1) one [maxgate][datalen]
+    //      block per slot; RF runs a second volume (imaginary part) of the same shape.
+    double* d_re = NULL, *d_im = NULL;              // working copies: the accumulators stay untouched, the session may keep adding to them
 
-        if (nodal) {
-            CU(cudaMallocAsync(&d_out, sizeof(double) * n, s->stream));
-            CU(cudaMemsetAsync(d_out, 0, sizeof(double) * n, s->stream));
-            CUK(mmcb_k_spread_nodes(s->d_field, d_out, s->d_elem, m.ne, m.nn, maxgate, srcnum, s->stream));
-            d_src = d_out;
-        } else if (!s->acc_double) {
-            CU(cudaMallocAsync(&d_out, sizeof(double) * n, s->stream));
-            CUK(mmcb_k_acc_to_double(s->d_field, d_out, n, s->stream));
-            d_src = d_out;
+    if (out->field) {
+        const bool nodal = (!s->isgrid && !s->ishp && c.basisorder);    // BLB deposits per element; nodal output is spread here
+        const bool rf = s->cfg.isrf && s->d_field_im;
+        const int nslots = s->cfg.nslots, datalen = s->cfg.datalen, maxgate = s->cfg.maxgate, srcnum = c.srcnum;
+        const size_t n = s->fieldlen, n1 = (size_t)datalen * maxgate * srcnum;      // whole volume / block of the first slot
+        const double* src_re = (const double*)s->d_field, *src_im = rf ? (const double*)s->d_field_im : NULL;
+        auto working_copy = [&](const void* acc, double** d, const double** src, bool force) -> int {
+            if (nodal) {            // slot blocks are consecutive gate blocks of the same stride: maxgate * nslots "gates"
+                CU(cudaMallocAsync(d, sizeof(double) * n, s->stream));
+                CU(cudaMemsetAsync(*d, 0, sizeof(double) * n, s->stream));
+                CUK(mmcb_k_spread_nodes(acc, *d, s->d_elem, m.ne, m.nn, maxgate * nslots, srcnum, s->stream));
+            } else if (!s->acc_double) {
+                CU(cudaMallocAsync(d, sizeof(double) * n, s->stream));
+                CUK(mmcb_k_acc_to_double(acc, *d, n, s->stream));
+            } else if (force) {
+                CU(cudaMallocAsync(d, sizeof(double) * n, s->stream));
+                CU(cudaMemcpyAsync(*d, acc, sizeof(double) * n, cudaMemcpyDeviceToDevice, s->stream));
+            } else {
+                return 0;
+            }
+
+            *src = *d;
+            return 0;
+        };
+
+        if (working_copy(s->d_field, &d_re, &src_re, c.isnormalized != 0) || (rf && working_copy(s->d_field_im, &d_im, &src_im, c.isnormalized != 0))) {
+            return g_code;
         }
 
         if (c.isnormalized) {
-            if (!d_out) {       // the accumulators stay untouched: the session may keep adding to them
-                CU(cudaMallocAsync(&d_out, sizeof(double) * n, s->stream));
-            }
-
             const bool replay = (c.seed == MMCB_SEED_FROM_FILE && (c.outputtype == MMCB_OT_JACOBIAN || c.outputtype == MMCB_OT_WL || c.outputtype == MMCB_OT_WP));
             const bool basis1 = (!s->isgrid && c.basisorder), basis0 = (!s->isgrid && !c.basisorder);
-            const bool needdep = !replay && c.outputtype != MMCB_OT_ENERGY && !s->isgrid;
+            const bool needdep = !replay && c.outputtype != MMCB_OT_ENERGY && !s->isgrid;       // the energy-deposit sum of :2213-2260
+            const bool im1 = rf && srcnum == 1;         // mesh_normalize's imag_slot
             double fac[16], dep[MMCB_MAX_SRCNUM];
             double* d_dep = NULL;
             float* d_evol = NULL, *d_emua = NULL, *d_nvol = NULL;
+
+            if (basis1 && (needdep || nslots > srcnum) && rc_dev_alloc_float(&d_nvol, m.nvol, s->stream)) {
+                return g_code;
+            }
 
             if (needdep) {
                 std::vector<float> emua(m.ne);
@@ -2129,20 +2055,16 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
                 CU(cudaMallocAsync(&d_dep, sizeof(double) * MMCB_MAX_SRCNUM, s->stream));
                 CU(cudaMemsetAsync(d_dep, 0, sizeof(double) * MMCB_MAX_SRCNUM, s->stream));
 
-                if (basis1) {
-                    if (rc_dev_alloc_float(&d_nvol, m.nvol, s->stream)) {
-                        return g_code;
+                if (basis1) {       // W /= nvol, then sum_e (sum over gates and the 4 nodes of |phi|) evol mua
+                    CUK(mmcb_k_norm_nvol(d_re, n1, m.nn, srcnum, d_nvol, s->stream));
+
+                    if (im1) {
+                        CUK(mmcb_k_norm_nvol(d_im, n1, m.nn, srcnum, d_nvol, s->stream));
                     }
 
-                    if (d_src != d_out) {
-                        CU(cudaMemcpyAsync(d_out, d_src, sizeof(double) * n, cudaMemcpyDeviceToDevice, s->stream));
-                        d_src = d_out;
-                    }
-
-                    CUK(mmcb_k_norm_nvol(d_out, n, m.nn, srcnum, d_nvol, s->stream));
-                    CUK(mmcb_k_norm_elemdep(d_out, s->d_elem, d_evol, d_emua, m.ne, m.nn, maxgate, srcnum, d_dep, s->stream));
+                    CUK(mmcb_k_norm_elemdep(d_re, im1 ? d_im : NULL, s->d_elem, d_evol, d_emua, m.ne, m.nn, maxgate, srcnum, d_dep, s->stream));
                 } else {
-                    CUK(mmcb_k_norm_sum(d_src, n / srcnum, srcnum, d_dep, s->stream));
+                    CUK(mmcb_k_norm_sum(d_re, n1 / srcnum, srcnum, d_dep, s->stream));
                 }
 
                 CU(cudaMemcpyAsync(dep, d_dep, sizeof(double) * MMCB_MAX_SRCNUM, cudaMemcpyDeviceToHost, s->stream));
@@ -2182,9 +2104,46 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
             }
 
             out->normalizer = sum / srcnum;
-            const bool divide = needdep && basis0;
-            CUK(mmcb_k_norm_scale(d_src, d_out, n, datalen, srcnum, divide ? d_evol : NULL, divide ? d_emua : NULL, fac, s->stream));
-            d_src = d_out;
+            const bool divide = needdep && basis0;      // basisorder 0: every entry is divided by evol * mua first
+            CUK(mmcb_k_norm_scale(d_re, d_re, n1, datalen, srcnum, divide ? d_evol : NULL, divide ? d_emua : NULL, fac, s->stream));
+
+            if (im1 && !(replay || c.outputtype == MMCB_OT_ENERGY)) {
+                // both parts of one complex fluence get the same factors; the reference leaves the imaginary part of a per-element
+                // volume undivided (src/mmc_mesh.c:2250-2256), which cannot be intended.  The factor is rounded to float (:2268-2270)
+                double facf[16];
+
+                for (int j = 0; j < 16; j++) {
+                    facf[j] = (double)(float)fac[j];
+                }
+
+                CUK(mmcb_k_norm_scale(d_im, d_im, n1, datalen, srcnum, divide ? d_evol : NULL, divide ? d_emua : NULL, facf, s->stream));
+            }
+
+            if (n > n1) {           // the slots behind the first: nodal-volume division and the average normaliser (src/mmc_cu_host.cu:997-1060)
+                double all[16];
+
+                for (int j = 0; j < 16; j++) {
+                    all[j] = out->normalizer;
+                }
+
+                if (basis1) {
+                    CUK(mmcb_k_norm_nvol(d_re + n1, n - n1, m.nn, srcnum, d_nvol, s->stream));
+                }
+
+                CUK(mmcb_k_norm_scale(d_re + n1, d_re + n1, n - n1, datalen, srcnum, NULL, NULL, all, s->stream));
+
+                if (rf) {
+                    for (int j = 0; j < 16; j++) {
+                        all[j] = (double)(float)out->normalizer;
+                    }
+
+                    if (basis1) {
+                        CUK(mmcb_k_norm_nvol(d_im + n1, n - n1, m.nn, srcnum, d_nvol, s->stream));
+                    }
+
+                    CUK(mmcb_k_norm_scale(d_im + n1, d_im + n1, n - n1, datalen, srcnum, NULL, NULL, all, s->stream));
+                }
+            }
 
             if (c.issaveref && !dref.empty()) {          // :2160-2167
                 const float nz = 1.f / (float)out->energytot[0];
@@ -2202,141 +2161,45 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
         }
 
         tr.mark("fetch: normalise (device)");
-
-        if (out->overwrite) {
-            CU(cudaMemcpyAsync(out->field, d_src, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
-            CU(cudaStreamSynchronize(s->stream));
-        } else {
-            std::vector<double> W(n);
-            CU(cudaMemcpyAsync(W.data(), d_src, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
-            CU(cudaStreamSynchronize(s->stream));
-
-            for (size_t i = 0; i < n; i++) {
-                out->field[i] += W[i];          // cfg->exportfield[i] += field[i]  (src/mmc_cu_host.cu:918-920)
-            }
-        }
-
-        if (d_out) {
-            cudaFreeAsync(d_out, s->stream);
-        }
-
-        tr.mark("fetch: volume D2H");
-    } else if (out->field) {
-        // raw sums -> double on the device (and elem->node spreading for nodal output), then one D2H copy per volume
-        const bool nodal = (!s->isgrid && !s->ishp && c.basisorder);
-        const int nslots = s->cfg.nslots;
-        auto download = [&](const void* d_src, std::vector<double>& W) -> int {
-            double* d_tmp = NULL;
-            W.resize(s->fieldlen);
-
-            if (nodal) {        // slot blocks are consecutive gate blocks of the same stride: maxgate*nslots "gates"
-                CU(cudaMallocAsync(&d_tmp, sizeof(double) * s->fieldlen, s->stream));
-                CU(cudaMemsetAsync(d_tmp, 0, sizeof(double) * s->fieldlen, s->stream));
-                CUK(mmcb_k_spread_nodes(d_src, d_tmp, s->d_elem, m.ne, m.nn, s->cfg.maxgate * nslots, c.srcnum, s->stream));
-                CU(cudaMemcpyAsync(W.data(), d_tmp, sizeof(double) * s->fieldlen, cudaMemcpyDeviceToHost, s->stream));
-            } else if (!s->acc_double) {
-                CU(cudaMallocAsync(&d_tmp, sizeof(double) * s->fieldlen, s->stream));
-                CUK(mmcb_k_acc_to_double(d_src, d_tmp, s->fieldlen, s->stream));
-                CU(cudaMemcpyAsync(W.data(), d_tmp, sizeof(double) * s->fieldlen, cudaMemcpyDeviceToHost, s->stream));
+        auto download = [&](const double* d, double* host) -> int {
+            if (out->overwrite) {
+                CU(cudaMemcpyAsync(host, d, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
+                CU(cudaStreamSynchronize(s->stream));
             } else {
-                CU(cudaMemcpyAsync(W.data(), d_src, sizeof(double) * s->fieldlen, cudaMemcpyDeviceToHost, s->stream));
-            }
+                std::vector<double> W(n);
+                CU(cudaMemcpyAsync(W.data(), d, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream));
+                CU(cudaStreamSynchronize(s->stream));
 
-            CU(cudaStreamSynchronize(s->stream));
-
-            if (d_tmp) {
-                cudaFreeAsync(d_tmp, s->stream);
+                for (size_t i = 0; i < n; i++) {
+                    host[i] += W[i];            // cfg->exportfield[i] += field[i]  (src/mmc_cu_host.cu:918-920)
+                }
             }
 
             return 0;
         };
-        std::vector<double> W, Wim;
-        int drc = download(s->d_field, W);
 
-        if (drc == 0 && s->cfg.isrf) {
-            drc = download(s->d_field_im, Wim);
-        }
-
-        if (drc) {
-            return drc;
+        if (download(src_re, out->field) || (rf && out->field_im && download(src_im, out->field_im))) {
+            return g_code;
         }
 
         tr.mark("fetch: volume D2H");
 
-        if (c.isnormalized) {
-            double sum = 0;
-
-            for (int j = 0; j < c.srcnum; j++) {
-                double eabs = out->energytot[j] - out->energyesc[j];       // src/mmc_cu_host.cu:988
-                sum += normalize_field(s, W.data(), (s->cfg.isrf && c.srcnum == 1) ? Wim.data() : NULL, j == 0 && !dref.empty() ? dref.data() : NULL,
-                                       (float)eabs, (float)out->energytot[j], j);
-            }
-
-            out->normalizer = sum / c.srcnum;
-
-            // the slots behind the first get the average normaliser (and the nodal-volume division), src/mmc_cu_host.cu:997-1060
-            if (nslots > c.srcnum) {
-                const size_t datalen = (size_t)s->cfg.datalen, stride = datalen * s->cfg.maxgate;
-                const bool basis1 = (!s->isgrid && c.basisorder);
-
-                for (int slot = c.srcnum; slot < nslots; slot++) {
-                    for (size_t k = 0; k < stride; k++) {
-                        const size_t idx = (size_t)slot * stride + k;
-
-                        if (basis1 && m.nvol[k % datalen] > 0.f) {
-                            W[idx] /= m.nvol[k % datalen];
-
-                            if (!Wim.empty()) {
-                                Wim[idx] /= m.nvol[k % datalen];
-                            }
-                        }
-
-                        W[idx] *= out->normalizer;
-
-                        if (!Wim.empty()) {
-                            Wim[idx] *= (float)out->normalizer;
-                        }
-                    }
-                }
-            }
-        }
-
-        for (size_t i = 0; i < s->fieldlen; i++) {
-            out->field[i] = (out->overwrite ? 0.0 : out->field[i]) + W[i];          // cfg->exportfield[i] += field[i]  (src/mmc_cu_host.cu:918-920)
-        }
-
-        if (out->field_im && !Wim.empty()) {
-            for (size_t i = 0; i < s->fieldlen; i++) {
-                out->field_im[i] = (out->overwrite ? 0.0 : out->field_im[i]) + Wim[i];
-            }
-        }
-
-        tr.mark("fetch: normalise+accumulate");
-
-        // ---- adjoint Jacobians from the slots' fluence (src/mmc_cu_host.cu:1063-1395): the normalised volumes go back to the
-        //      device as floats, one pass sums the gates per slot, the pair kernels write [datalen][Ns*Nd] per component
+        // ---- adjoint Jacobians from the slots' normalised fluence (src/mmc_cu_host.cu:1063-1395): float copies of the volumes, one pass
+        //      sums the gates per slot, the pair kernels write [datalen][Ns*Nd] per component
         if (out->jacob && s->cfg.adj_ns > 0 && s->cfg.adj_nd > 0) {
-            const int Ns = s->cfg.adj_ns, Nd = s->cfg.adj_nd, dual = s->cfg.adj_dual, rf = s->cfg.isrf;
+            const int Ns = s->cfg.adj_ns, Nd = s->cfg.adj_nd, dual = s->cfg.adj_dual;
             const size_t N = (size_t)s->cfg.datalen, adjlen = N * Ns * Nd, single = adjlen * (rf ? 2 : 1);
-            std::vector<float> hf(s->fieldlen);
             float* d_f = NULL, *d_cwr = NULL, *d_cwi = NULL, *d_j1 = NULL, *d_j2 = NULL, *d_evol = NULL, *d_nvol = NULL;
-            CU(cudaMallocAsync(&d_f, sizeof(float) * s->fieldlen, s->stream));
+            CU(cudaMallocAsync(&d_f, sizeof(float) * n, s->stream));
             CU(cudaMallocAsync(&d_cwr, sizeof(float) * N * nslots, s->stream));
 
             for (int part = 0; part < (rf ? 2 : 1); part++) {
-                const std::vector<double>& src = part ? Wim : W;
-
-                for (size_t i = 0; i < s->fieldlen; i++) {
-                    hf[i] = (float)src[i];
-                }
-
                 if (part) {
                     CU(cudaMallocAsync(&d_cwi, sizeof(float) * N * nslots, s->stream));
                 }
 
-                CU(cudaMemcpyAsync(d_f, hf.data(), sizeof(float) * s->fieldlen, cudaMemcpyHostToDevice, s->stream));
+                CUK(mmcb_k_double_to_float(part ? src_im : src_re, d_f, n, s->stream));
                 CUK(mmcb_k_adj_cw(d_f, part ? d_cwi : d_cwr, N, s->cfg.maxgate, nslots, s->stream));
-                CU(cudaStreamSynchronize(s->stream));       // hf is reused
             }
 
             const bool want_mua = (c.outputtype == MMCB_OT_ADJOINT || dual), want_d = (c.outputtype != MMCB_OT_ADJOINT);
@@ -2401,6 +2264,12 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
             }
 
             tr.mark("fetch: adjoint Jacobian");
+        }
+
+        for (double* q : {d_re, d_im}) {
+            if (q) {
+                cudaFreeAsync(q, s->stream);
+            }
         }
     }
 

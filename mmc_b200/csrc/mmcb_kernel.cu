@@ -867,7 +867,7 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
 
     int gate;
 
-    if (GENERAL && (gp.outputtype == 4 || gp.outputtype == 5)) {
+    if (GENERAL && gp.isreplay && (gp.outputtype == 4 || gp.outputtype == 5)) {
         gate = min((int)(a.replaytime[p.id] * gp.Rtstep), gp.maxgate - 1);
     } else {
         gate = min((int)((p.t - gp.tstart) * gp.Rtstep), gp.maxgate - 1);
@@ -1223,7 +1223,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
             float ww = currweight - p.w;
             p.t = tnew;
 
-            if (GENERAL && (gp.outputtype == 4 || gp.outputtype == 5)) {
+            if (GENERAL && gp.isreplay && (gp.outputtype == 4 || gp.outputtype == 5)) {
                 gate = min((int)(a.replaytime[p.id] * gp.Rtstep), gp.maxgate - 1);
             }
 

@@ -365,28 +365,45 @@ __global__ void mmcb_norm_nvol_kernel(double* __restrict__ W, size_t n, int nn, 
     }
 }
 
-// basisorder 1, step 2: energydeposit[pair] = sum_e (sum_gates sum_4nodes (float)W) * evol_e * mua_e (:2224-2245)
-__global__ void mmcb_norm_elemdep_kernel(const double* __restrict__ W, const int* __restrict__ elem, const float* __restrict__ evol,
-        const float* __restrict__ emua, int ne, int nn, int maxgate, int srcnum, double* __restrict__ dep) {
+// basisorder 1, step 2: energydeposit[pair] = sum_e (sum_gates sum_4nodes (float)W) * evol_e * mua_e (:2224-2245); with an imaginary
+// volume (RF, one pattern) the summand is |phi| = sqrtf(re^2 + im^2) (:2232-2237)
+__global__ void mmcb_norm_elemdep_kernel(const double* __restrict__ W, const double* __restrict__ Wim, const int* __restrict__ elem,
+        const float* __restrict__ evol, const float* __restrict__ emua, int ne, int nn, int maxgate, int srcnum, double* __restrict__ dep) {
     const int p = blockIdx.y;
     double s = 0.0;
 
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x) {
         const int4 ee = *(const int4*)(elem + 4 * (size_t)e);
+        const int id[4] = {ee.x, ee.y, ee.z, ee.w};
         double energyelem = 0.0;
 
         for (int g = 0; g < maxgate; g++) {
             const size_t base = (size_t)g * nn;
-            energyelem += (float)W[(base + ee.x - 1) * srcnum + p];
-            energyelem += (float)W[(base + ee.y - 1) * srcnum + p];
-            energyelem += (float)W[(base + ee.z - 1) * srcnum + p];
-            energyelem += (float)W[(base + ee.w - 1) * srcnum + p];
+            #pragma unroll
+
+            for (int k = 0; k < 4; k++) {
+                const size_t at = (base + id[k] - 1) * srcnum + p;
+                const float re = (float)W[at];
+
+                if (Wim) {
+                    const float im = (float)Wim[at];
+                    energyelem += sqrtf(re * re + im * im);
+                } else {
+                    energyelem += re;
+                }
+            }
         }
 
         s += energyelem * evol[e] * emua[e];
     }
 
     block_add(s, dep + p);
+}
+
+__global__ void mmcb_double_to_float_kernel(const double* __restrict__ in, float* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        out[i] = (float)in[i];
+    }
 }
 
 // final pass: out = (in / (evol*mua)) * fac[pair]   (division only for basisorder 0, :2252-2258), out may alias in
@@ -415,10 +432,15 @@ extern "C" int mmcb_k_norm_nvol(double* W, size_t n, int nn, int srcnum, const f
     return (int)cudaGetLastError();
 }
 
-extern "C" int mmcb_k_norm_elemdep(const double* W, const int* elem, const float* evol, const float* emua, int ne, int nn, int maxgate, int srcnum,
-                                   double* dep, cudaStream_t st) {
+extern "C" int mmcb_k_norm_elemdep(const double* W, const double* Wim, const int* elem, const float* evol, const float* emua, int ne, int nn, int maxgate,
+                                   int srcnum, double* dep, cudaStream_t st) {
     dim3 g(grid_for((size_t)ne), srcnum);
-    mmcb_norm_elemdep_kernel<<<g, 256, 0, st>>>(W, elem, evol, emua, ne, nn, maxgate, srcnum, dep);
+    mmcb_norm_elemdep_kernel<<<g, 256, 0, st>>>(W, Wim, elem, evol, emua, ne, nn, maxgate, srcnum, dep);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int mmcb_k_double_to_float(const double* in, float* out, size_t n, cudaStream_t st) {
+    mmcb_double_to_float_kernel<<<grid_for(n), 256, 0, st>>>(in, out, n);
     return (int)cudaGetLastError();
 }
 

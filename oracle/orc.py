@@ -257,11 +257,12 @@ def write_mesh_files(dirname, tag, node, elem, etype, med, evol=None):
 
 
 def run_ref(node, elem, etype, med, *, nthread=1, cuda=False, extra_args=(), timeout=3600, keep_dir=None, evol=None, check=True,
-            expect="out.bin", multislot=False, **kw):
-    """Run oracle/_ref/mmc_ref (or mmc_refcuda) on the same inputs; returns dict(field, absorbed_frac, speed, ...)."""
+            expect="out.bin", multislot=False, binary=None, **kw):
+    """Run oracle/_ref/mmc_ref (or mmc_refcuda, or `binary`: e.g. the drop-in CLI oracle/_ref/mmc_b200cli) on the same inputs;
+    returns dict(field, absorbed_frac, speed, ...)."""
     p = dict(DEFAULTS)
     p.update(kw)
-    binp = REF_CUDA_MS_BIN if multislot else (REF_CUDA_BIN if cuda else REF_BIN)
+    binp = binary or (REF_CUDA_MS_BIN if multislot else (REF_CUDA_BIN if cuda else REF_BIN))
     tmp = keep_dir or tempfile.mkdtemp(prefix="mmcref_")
     os.makedirs(tmp, exist_ok=True)
     tag = "t"

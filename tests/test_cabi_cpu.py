@@ -87,6 +87,9 @@ def test_config_validation_mirrors_reference_messages():
     bad = dict(cfg, srcpos=(-5, 0, 0))
     with pytest.raises(mmc_b200.MMCError, match="does not enclose"):
         api.Problem(bad).sizes()
+    for ot in ("jacobian", "wl", "wp"):          # src/mmc_utils.c:4266-4268: replay outputs need the seeds of an .mch file
+        with pytest.raises(mmc_b200.MMCError, match="only valid in the reply mode"):
+            api.Problem(dict(cfg, outputtype=ot)).sizes()
     g = api.Problem(dict(cfg, method="grid", steps=(0.5, 0.5, 0.5))).sizes()
     assert tuple(g.dim) == (41, 41, 41) and g.datalen == 41 ** 3        # mesh_createdualmesh, src/mmc_mesh.c:374-380
 

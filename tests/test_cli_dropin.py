@@ -99,6 +99,52 @@ def test_reference_cli_writes_adjoint_jacobians_through_the_b200_engine(tmp_path
             assert lit.sum() > 5 and np.median(rel) < 0.15 and cc > 0.97, (name, pair, np.median(rel), cc)
 
 
+@needs_cli
+@pytest.mark.gpu
+def test_cli_length_unit_is_applied_once():
+    """`-u 0.5`: the reference host multiplies mua/mus by the unit before mmc_run_cu (src/mmc_mesh.c:542-546); the stub must hand the
+    engine media that end up scaled ONCE.  Same binary, same command line: `-c cuda` (this engine) against `-c sse` (reference CPU)
+    and against the CPU oracle."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cases
+    import orc
+    node, elem, et, med = cases.two_media_cube()
+    kw = cases.case_kwargs("blb_elem_reflect")
+    kw.update(nphoton=300000, unitinmm=0.5)
+    gpu = orc.run_ref(node, elem, et, med, binary=CLI, cuda=True, **kw)
+    cpu = orc.run_ref(node, elem, et, med, binary=CLI, nthread=os.cpu_count() or 1, **kw)
+    assert "MMC-B200" in gpu["log"]
+    one = orc.run_ref(node, elem, et, med, binary=CLI, cuda=True, **dict(kw, unitinmm=1.0))
+    assert abs(gpu["absorbed_frac"] - cpu["absorbed_frac"]) < 4e-3, (gpu["absorbed_frac"], cpu["absorbed_frac"])
+    assert abs(one["absorbed_frac"] - gpu["absorbed_frac"]) > 0.02          # the unit matters on this problem
+    fg, fc = gpu["field_flat"], cpu["field_flat"]
+    fg, fc = np.where(np.isfinite(fg), fg, 0), np.where(np.isfinite(fc), fc, 0)
+    assert abs(fg.sum() / fc.sum() - 1) < 0.02                              # normalisation carries unitinmm^3 (src/mmc_mesh.c:2206)
+
+
+@needs_cli
+@pytest.mark.gpu
+def test_cli_widefield_source_and_detector_labels_survive_the_host():
+    """Planar source over tets labelled -1 and a wide-field detector layer labelled -2 (examples/replaywide/createmesh.m:11-29): the
+    reference host moves the -1 labels into mesh->srcelem and turns -2 into prop+1 before mmc_run_cu (src/mmc_mesh.c:390-427); the stub
+    restores both for the engine.  Checked against the reference CPU path of the same binary: absorbed fraction, detected count."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cases
+    import orc
+    node, elem, et, med = cases.case_mesh("planar_widedet")
+    kw = cases.case_kwargs("planar_widedet")
+    kw.update(nphoton=300000)
+    gpu = orc.run_ref(node, elem, et, med, binary=CLI, cuda=True, **kw)
+    cpu = orc.run_ref(node, elem, et, med, binary=CLI, nthread=os.cpu_count() or 1, **kw)
+    assert "MMC-B200" in gpu["log"]
+    assert abs(gpu["absorbed_frac"] - cpu["absorbed_frac"]) < 4e-3, (gpu["absorbed_frac"], cpu["absorbed_frac"])
+    ng, nc = gpu["detectedcount"], cpu["detectedcount"]
+    assert nc > 1000 and abs(ng - nc) < 6 * nc ** 0.5 + 5, (ng, nc)
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference headers (this container only)")
 @pytest.mark.parametrize("flavour", [[], ["-DMCX_CONTAINER"]])
 def test_stub_compiles_against_the_reference_headers(flavour, tmp_path):

@@ -98,7 +98,20 @@ void run_red(uint32_t n, int threads_per_sm, int steps, uint32_t hotmask, const 
     cudaFree(d);
 }
 
-int main() {
+// usage: microbench                      the whole sweep
+//        microbench quick NREC NVOL [DEV] the two ceilings bench.py quotes: random 96-byte record gathers (256-bit loads) from a table of
+//                                         NREC records, random f64 reductions into a volume of NVOL accumulators (one line each)
+int main(int argc, char** argv) {
+    if (argc >= 4 && argv[1][0] == 'q') {
+        if (argc >= 5) {
+            CK(cudaSetDevice(atoi(argv[4])));
+        }
+
+        run_gather<96, 256>(atoi(argv[2]), 96, 1024, 2000);
+        run_red<double>((uint32_t)strtoul(argv[3], NULL, 10), 1024, 2000, 0, "f64");
+        return 0;
+    }
+
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
     printf("{\"device\":\"%s\",\"sm\":%d,\"l2_MB\":%.1f,\"clock_MHz\":%d}\n", p.name, p.multiProcessorCount, p.l2CacheSize / 1e6, p.clockRate / 1000);
     const int steps = 2000;
