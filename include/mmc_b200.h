@@ -222,6 +222,17 @@ void mmcb_destroy(mmcb_session* s);
  * the caller sizes its output arrays from the session and the mesh is prepared once (mmcb_query_sizes prepares it a second time) */
 int mmcb_run_session(mmcb_session* s, mmcb_output* out);
 
+/* ---- photon sharding over the GPUs of one box: the fan-out of mmc_run_cu over cfg->deviceid / cfg->workload
+ * (src/mmc_cu_host.cu:403-429,1538-1553).  `devices`: ndev distinct CUDA ordinals (0-based); `workload`: ndev relative weights or NULL
+ * (equal shares); device g simulates nphoton * w_g / sum(w) photons (the last one takes the remainder) with its own seeds
+ * (srand(seed + 7919 g); replay runs shard the photon index range instead).  One host thread and one session per device, no collective in
+ * the walk; afterwards NCCL (libnccl.so.2, loaded on first use) sum-reduces the volume(s) and the diffuse reflectance to devices[0] and
+ * gathers the detected-photon rows, seeds and trajectory records behind devices[0]'s own, truncated at maxdetphoton / maxjumpdebug like
+ * :823-853; the result is normalised and downloaded once.  ndev == 1 is mmcb_run_simulation.  out->kernel_ms = the slowest device. */
+int  mmcb_run_multi(const mmcb_config* cfg, const mmcb_mesh* mesh, int ndev, const int* devices, const float* workload, mmcb_output* out);
+/* the photon split mmcb_run_multi uses (exposed for callers that drive the devices themselves, and for tests) */
+void mmcb_photon_shares(uint64_t nphoton, int ndev, const float* workload, uint64_t* share);
+
 /* ---- host-side mesh helpers (what mmc_prep/tracer_prep compute; exposed for callers and tests) ------- */
 int mmcb_mesh_volumes(int nn, const float* node, int ne, int* elem_inout, const int* type, float* evol, float* nvol); /* mesh_getvolume src/mmc_mesh.c:910 */
 int mmcb_mesh_facenb(int ne, const int* elem, int* facenb);                                                           /* mesh_getfacenb src/mmc_highorder.cpp:124 */

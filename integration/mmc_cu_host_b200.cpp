@@ -232,16 +232,49 @@ extern "C" void mmc_run_cu(mcconfig* cfg, tetmesh* mesh, raytracer* tracer) {
     c.nodemua = (cfg->isnodalmua && cfg->nodemua) ? cfg->nodemua : NULL;          // src/mmc_cu_host.cu:477-487
     c.nodemusp = (c.nodemua && cfg->isnodalmusp && cfg->nodemusp) ? cfg->nodemusp : NULL;
 
-    // one session: the mesh is prepared once (face neighbours and tracer tables on the device), the output arrays are sized from it
-    int device = (cfg->deviceid[0] > 0 ? cfg->deviceid[0] : 1) - 1;    // the first enabled GPU; more GPUs: mmc_b200/multigpu.py
-    mmcb_session* sess = mmcb_create(&c, &m, device);
+    // devices: mcx_list_cu_gpu rewrote cfg->deviceid to the 1-based ids of the enabled GPUs (src/mmc_cu_host.cu:136-142).  One GPU: one
+    // session (the mesh is prepared once, the output arrays are sized from it).  Several GPUs (-G 1101, -W a,b,c): the library shards
+    // the photons by cfg->workload and merges the results over NCCL (mmcb_run_multi), which is the reference's omp fan-out (:1538-1553)
+    std::vector<int> devices;
+    std::vector<float> workload;
 
-    if (!sess) {
-        B200_ASSERT(-1);
+    for (unsigned int i = 0; i < activedev && cfg->deviceid[i] > 0; i++) {
+        devices.push_back(cfg->deviceid[i] - 1);
+        workload.push_back(cfg->workload[i]);
     }
 
+    if (devices.empty()) {
+        devices.push_back(0);
+        workload.push_back(1.f);
+    }
+
+    float fullload = 0.f;
+
+    for (float w : workload) {
+        fullload += w;
+    }
+
+    if (fullload < 1e-6f) {         // unspecified: proportional to the core count (:407-412) -- equal on one box of identical GPUs
+        for (size_t i = 0; i < workload.size(); i++) {
+            workload[i] = (float)gpuinfo[devices[i]].core;
+        }
+    }
+
+    const bool multi = devices.size() > 1;
+    mmcb_session* sess = NULL;
     mmcb_sizes sz;
-    B200_ASSERT(mmcb_get_sizes(sess, &sz));
+
+    if (multi) {
+        B200_ASSERT(mmcb_query_sizes(&c, &m, &sz));
+    } else {
+        sess = mmcb_create(&c, &m, devices[0]);
+
+        if (!sess) {
+            B200_ASSERT(-1);
+        }
+
+        B200_ASSERT(mmcb_get_sizes(sess, &sz));
+    }
 
     // ---- outputs (ownership as in src/mmc_cu_host.cu:339-367: exportfield defaults to mesh->weight; detected rows and
     //      seeds are malloc'ed here and freed by the caller)
@@ -305,13 +338,27 @@ extern "C" void mmc_run_cu(mcconfig* cfg, tetmesh* mesh, raytracer* tracer) {
     }
 
     MMC_FPRINTF(cfg->flog, "- code name: [MMC-B200] sm_100a photon engine (libmmc_b200 %x)\n", mmcb_version());
-    MMC_FPRINTF(cfg->flog, "- [device %d(1): %s] np=%.1f maxgate=%d repetition=%d\n", gpuinfo[0].id, gpuinfo[0].name,
-                (double)cfg->nphoton, sz.maxgate, cfg->respin);
+    {
+        std::vector<uint64_t> share(devices.size());
+        mmcb_photon_shares((uint64_t)cfg->nphoton, (int)devices.size(), workload.data(), share.data());
+
+        for (size_t i = 0; i < devices.size(); i++) {
+            MMC_FPRINTF(cfg->flog, "- [device %d(%d): %s] np=%.1f maxgate=%d repetition=%d\n", gpuinfo[devices[i]].id, (int)i + 1, gpuinfo[devices[i]].name,
+                        (double)share[i], sz.maxgate, cfg->respin);
+        }
+    }
+
     MMC_FPRINTF(cfg->flog, "lauching mmc_main_loop for time window [%.1fns %.1fns] ...\n", cfg->tstart * 1e9, cfg->tend * 1e9);
     mcx_fflush(cfg->flog);
     unsigned int tic = StartTimer();
-    B200_ASSERT(mmcb_run_session(sess, &out));
-    mmcb_destroy(sess);
+
+    if (multi) {
+        B200_ASSERT(mmcb_run_multi(&c, &m, (int)devices.size(), devices.data(), workload.data(), &out));
+    } else {
+        B200_ASSERT(mmcb_run_session(sess, &out));
+        mmcb_destroy(sess);
+    }
+
     unsigned int toc = GetTimeMillis() - tic;
     MMC_FPRINTF(cfg->flog, "kernel complete:  \t%d ms\nretrieving flux ... \t", (int)(out.kernel_ms + 0.5f));
     MMC_FPRINTF(cfg->flog, "transfer complete:        %d ms\n", toc);

@@ -101,7 +101,8 @@ class DevPtrs(C.Structure):
 EXPORTS = ["mmcb_version", "mmcb_last_error", "mmcb_list_gpu", "mmcb_query_sizes", "mmcb_run_simulation",
            "mmcb_create", "mmcb_set_field_buffer", "mmcb_launch", "mmcb_sync", "mmcb_last_kernel_ms",
            "mmcb_get_devptrs", "mmcb_get_sizes", "mmcb_fetch", "mmcb_reset", "mmcb_destroy", "mmcb_get_tables", "mmcb_run_session",
-           "mmcb_mesh_volumes", "mmcb_mesh_facenb", "mmcb_mesh_initelem", "mmcb_host_seeds", "mmcb_rng_selftest"]
+           "mmcb_mesh_volumes", "mmcb_mesh_facenb", "mmcb_mesh_initelem", "mmcb_host_seeds", "mmcb_rng_selftest",
+           "mmcb_run_multi", "mmcb_photon_shares"]
 
 _lib = None
 
@@ -138,6 +139,9 @@ def lib():
         L.mmcb_host_seeds.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_void_p]
         L.mmcb_host_seeds.restype = None
         L.mmcb_rng_selftest.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.mmcb_run_multi.argtypes = [C.POINTER(Config), C.POINTER(Mesh), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Output)]
+        L.mmcb_photon_shares.argtypes = [C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+        L.mmcb_photon_shares.restype = None
         _lib = L
     return _lib
 
@@ -434,6 +438,31 @@ def run_onecall(cfg):
     sz = prob.sizes()
     buf = _OutBuffers(prob, sz)
     _check(lib().mmcb_run_simulation(C.byref(prob.cfg), C.byref(prob.mesh), prob.device, C.byref(buf.out)))
+    return buf.result(prob)
+
+
+def photon_shares(nphoton, ndev, workload=None):
+    """Photons per device as mmcb_run_multi splits them (reference rule: src/mmc_cu_host.cu:403-429)."""
+    out = np.zeros(ndev, dtype=np.uint64)
+    w = None if workload is None else np.ascontiguousarray(workload, dtype=np.float32)
+    lib().mmcb_photon_shares(int(nphoton), int(ndev), None if w is None else w.ctypes.data, out.ctypes.data)
+    return out
+
+
+def run_multi(cfg, gpuids=None, workload=None):
+    """One simulation sharded over several GPUs of this box inside the library (mmcb_run_multi): `gpuids` are 1-based like cfg['gpuid']
+    (default: every GPU), `workload` the relative shares (cfg['workload'] of pmmc, `-W` of the command line)."""
+    prob = Problem(cfg)
+    if gpuids is None:
+        gpuids = [g["id"] for g in gpuinfo()]
+    dev = np.ascontiguousarray([int(g) - 1 for g in gpuids], dtype=np.int32)
+    w = None if workload is None else np.ascontiguousarray(workload, dtype=np.float32)
+    if w is not None and len(w) != len(dev):
+        raise MMCError(-2, "workload needs one entry per GPU")
+    sz = prob.sizes()
+    buf = _OutBuffers(prob, sz)
+    _check(lib().mmcb_run_multi(C.byref(prob.cfg), C.byref(prob.mesh), len(dev), dev.ctypes.data, None if w is None else w.ctypes.data,
+                                C.byref(buf.out)))
     return buf.result(prob)
 
 

@@ -5,6 +5,8 @@
 // initial-element search, exterior-face numbering, surface nodal-volume correction, normalisation.
 // The tables are repacked into the structure-of-records layout of mmcb_types.h before upload.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>           // types only: the library is resolved with dlopen at the first multi-GPU run
 
 #include <algorithm>
 #include <cmath>
@@ -14,6 +16,7 @@
 #include <chrono>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mmc_b200.h"
@@ -2333,6 +2336,337 @@ int mmcb_run_simulation(const mmcb_config* cfg, const mmcb_mesh* mesh, int devic
     mmcb_destroy(s);
     g_err = keep;
     tr.mark("run: destroy");
+    return rc;
+}
+
+// -----------------------------------------------------------------------------------------------------------------------------------
+// Photon sharding over the GPUs of one box: what mmc_run_cu does with cfg->deviceid / cfg->workload (src/mmc_cu_host.cu:403-429,
+// 1538-1553: one host thread per GPU, photons split by workload, results merged under omp critical).  Here: one host thread and one
+// session per device for the walk -- no data-path collective --, then an epilogue over NVLink: ncclReduce of the accumulator
+// volume(s) and the diffuse reflectance to the first device, the detected-photon rows and seeds gathered behind the first device's
+// own rows (counts first, then payload, truncated at maxdetphoton like :823-853), energy tallies summed on the host, and ONE
+// normalisation + download from the first device.  NCCL is resolved with dlopen (libnccl.so.2) so that single-GPU users need none.
+// -----------------------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct NcclApi {
+    void* lib = NULL;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = NULL;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = NULL;
+    ncclResult_t (*GroupStart)() = NULL;
+    ncclResult_t (*GroupEnd)() = NULL;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = NULL;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = NULL;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = NULL;
+    const char* (*GetErrorString)(ncclResult_t) = NULL;
+
+    int load() {
+        if (lib) {
+            return 0;
+        }
+
+        const char* names[] = {getenv("MMCB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+
+        for (const char* n : names) {
+            if (n && (lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) {
+                break;
+            }
+        }
+
+        if (!lib) {
+            return fail(MMCB_ERR_CUDA, "multi-GPU runs need NCCL: libnccl.so.2 could not be loaded (%s)", dlerror());
+        }
+
+#define NCCL_SYM(field, name) do { *(void**)(&field) = dlsym(lib, name); if (!field) return fail(MMCB_ERR_CUDA, "NCCL symbol %s is missing", name); } while (0)
+        NCCL_SYM(CommInitAll, "ncclCommInitAll");
+        NCCL_SYM(CommDestroy, "ncclCommDestroy");
+        NCCL_SYM(GroupStart, "ncclGroupStart");
+        NCCL_SYM(GroupEnd, "ncclGroupEnd");
+        NCCL_SYM(Reduce, "ncclReduce");
+        NCCL_SYM(Send, "ncclSend");
+        NCCL_SYM(Recv, "ncclRecv");
+        NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef NCCL_SYM
+        return 0;
+    }
+};
+
+NcclApi g_nccl;
+#define NC(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(MMCB_ERR_CUDA, "NCCL error %d (%s) at %s:%d", (int)r_, g_nccl.GetErrorString(r_), __FILE__, __LINE__); } while (0)
+
+// photons of device g: nphoton * w_g / sum(w), the last device takes the remainder (the reference truncates every share, :425-429)
+std::vector<uint64_t> photon_shares(uint64_t nphoton, int ndev, const float* workload) {
+    std::vector<double> w(ndev, 1.0);
+    double total = 0;
+
+    for (int g = 0; g < ndev; g++) {
+        if (workload && workload[g] > 0.f) {
+            w[g] = workload[g];
+        }
+
+        total += w[g];
+    }
+
+    std::vector<uint64_t> share(ndev);
+    uint64_t given = 0;
+
+    for (int g = 0; g < ndev; g++) {
+        share[g] = (g == ndev - 1) ? nphoton - given : (uint64_t)((double)nphoton * w[g] / total);
+        given += share[g];
+    }
+
+    return share;
+}
+
+}   // namespace
+
+void mmcb_photon_shares(uint64_t nphoton, int ndev, const float* workload, uint64_t* share) {
+    const std::vector<uint64_t> v = photon_shares(nphoton, ndev, workload);
+    std::copy(v.begin(), v.end(), share);
+}
+
+int mmcb_run_multi(const mmcb_config* cfg, const mmcb_mesh* mesh, int ndev, const int* devices, const float* workload, mmcb_output* out) {
+    if (!cfg || !mesh || !out || ndev < 1 || !devices) {
+        return fail(MMCB_ERR_INPUT, "null argument or no device");
+    }
+
+    if (ndev == 1) {
+        return mmcb_run_simulation(cfg, mesh, devices[0], out);
+    }
+
+    for (int g = 0; g < ndev; g++)
+        for (int h = 0; h < g; h++)
+            if (devices[g] == devices[h]) {
+                return fail(MMCB_ERR_INPUT, "device %d is listed twice", devices[g]);
+            }
+
+    if (workload)
+        for (int g = 0; g < ndev; g++)
+            if (!(workload[g] >= 0.f)) {
+                return fail(MMCB_ERR_INPUT, "workload was unspecified for an active device");       // src/mmc_cu_host.cu:420-422
+            }
+
+    if (g_nccl.load()) {
+        return g_code;
+    }
+
+    Trace tr;
+    const std::vector<uint64_t> share = photon_shares(cfg->nphoton, ndev, workload);
+    std::vector<uint64_t> first(ndev, 0);
+
+    for (int g = 1; g < ndev; g++) {
+        first[g] = first[g - 1] + share[g - 1];
+    }
+
+    // ---- the walk: one thread and one session per device; replay runs shard the photon index range, the others draw their thread
+    //      seeds from their own host stream srand(seed + 7919 g) (slices of one stream would make every device generate and discard
+    //      the other devices' words)
+    std::vector<mmcb_session*> sess(ndev, (mmcb_session*)NULL);
+    std::vector<int> rcs(ndev, 0);
+    std::vector<std::string> errs(ndev);
+    std::vector<float> ms(ndev, 0.f);
+    std::vector<std::thread> workers;
+    const bool replay = (cfg->seed == MMCB_SEED_FROM_FILE);
+
+    for (int g = 0; g < ndev; g++) {
+        workers.emplace_back([&, g]() {
+            mmcb_config c = *cfg;
+            c.nphoton = share[g];
+
+            if (replay) {           // every session holds the whole seed table; the kernel indexes it with photon_offset + id
+                c.nphoton = cfg->nphoton;
+            }
+
+            mmcb_session* s = mmcb_create(&c, mesh, devices[g]);
+
+            if (!s) {
+                rcs[g] = g_code ? g_code : MMCB_ERR_CUDA;
+                errs[g] = g_err;
+                return;
+            }
+
+            sess[g] = s;
+            const int respin = s->cfg.c.respin;
+            const uint64_t mine = share[g], per = mine / respin;
+
+            for (int it = 0; it < respin && rcs[g] == 0 && mine > 0; it++) {
+                const uint64_t n = (it == respin - 1) ? mine - per * (respin - 1) : per;
+
+                if (n == 0) {
+                    continue;
+                }
+
+                rcs[g] = mmcb_launch(s, n, (replay ? first[g] : 0) + per * it, replay ? cfg->seed : cfg->seed + 7919 * g, it, NULL);
+
+                if (rcs[g] == 0) {
+                    rcs[g] = mmcb_sync(s);
+                }
+
+                ms[g] += s->last_ms;
+            }
+
+            if (rcs[g]) {
+                errs[g] = g_err;
+            }
+        });
+    }
+
+    for (std::thread& t : workers) {
+        t.join();
+    }
+
+    auto cleanup = [&]() {
+        for (mmcb_session* s : sess) {
+            if (s) {
+                session_free(s);
+            }
+        }
+    };
+
+    for (int g = 0; g < ndev; g++) {
+        if (rcs[g]) {
+            const std::string keep = errs[g];
+            const int code = rcs[g];
+            cleanup();
+            return fail(code, "device %d: %s", devices[g], keep.c_str());
+        }
+    }
+
+    tr.mark("multi: walk on all devices");
+    // ---- epilogue over NVLink
+    mmcb_session* s0 = sess[0];
+    const size_t accsize = s0->acc_double ? 8 : 4;
+    const ncclDataType_t acctype = s0->acc_double ? ncclDouble : ncclFloat;
+    std::vector<ncclComm_t> comm(ndev);
+    auto body = [&]() -> int {
+        NC(g_nccl.CommInitAll(comm.data(), ndev, devices));
+        // detector rows: counts first (host), then the payload behind the first device's rows
+        std::vector<unsigned int> cnt(ndev, 0);
+        std::vector<double> en(2 * MMCB_MAX_SRCNUM, 0.0);
+        double raytet = 0;
+
+        for (int g = 0; g < ndev; g++) {
+            double e[2 * MMCB_MAX_SRCNUM], r = 0;
+            CU(cudaSetDevice(devices[g]));
+            CU(cudaMemcpy(e, sess[g]->d_energy, sizeof(e), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(&r, sess[g]->d_raytet, sizeof(r), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(&cnt[g], sess[g]->d_detcount, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+
+            for (int j = 0; j < 2 * MMCB_MAX_SRCNUM; j++) {
+                en[j] += e[j];
+            }
+
+            raytet += r;
+        }
+
+        std::vector<unsigned int> tcnt(ndev, 0);
+
+        if (s0->d_traj) {
+            for (int g = 0; g < ndev; g++) {
+                CU(cudaSetDevice(devices[g]));
+                CU(cudaMemcpy(&tcnt[g], sess[g]->d_trajcount, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+            }
+        }
+
+        const unsigned int cap = s0->cfg.c.maxdetphoton;
+        const int reclen = s0->cfg.reclen;
+        NC(g_nccl.GroupStart());
+
+        for (int g = 0; g < ndev; g++) {        // volume(s) and diffuse reflectance: sum into the first device, in place
+            NC(g_nccl.Reduce(sess[g]->d_field, s0->d_field, s0->efieldlen, acctype, ncclSum, 0, comm[g], sess[g]->stream));
+
+            if (s0->d_field_im) {
+                NC(g_nccl.Reduce(sess[g]->d_field_im, s0->d_field_im, s0->efieldlen, acctype, ncclSum, 0, comm[g], sess[g]->stream));
+            }
+
+            if (s0->d_dref) {
+                NC(g_nccl.Reduce(sess[g]->d_dref, s0->d_dref, (size_t)s0->mesh.nf * s0->cfg.maxgate, ncclDouble, ncclSum, 0, comm[g], sess[g]->stream));
+            }
+        }
+
+        (void)accsize;
+        NC(g_nccl.GroupEnd());
+        unsigned long long total = std::min(cnt[0], cap), detected_all = cnt[0];
+
+        if (s0->isdet) {
+            NC(g_nccl.GroupStart());
+
+            for (int g = 1; g < ndev; g++) {
+                detected_all += cnt[g];
+                const unsigned int have = std::min(cnt[g], cap);                                     // rows that device stored
+                const unsigned int take = (unsigned int)std::min<unsigned long long>(have, cap - total); // rows that still fit (:823-834)
+
+                if (take > 0) {
+                    NC(g_nccl.Send(sess[g]->d_detected, (size_t)take * reclen, ncclFloat, 0, comm[g], sess[g]->stream));
+                    NC(g_nccl.Recv(s0->d_detected + (size_t)total * reclen, (size_t)take * reclen, ncclFloat, g, comm[0], s0->stream));
+
+                    if (s0->d_detseed) {
+                        NC(g_nccl.Send(sess[g]->d_detseed, (size_t)take * 2, ncclUint64, 0, comm[g], sess[g]->stream));
+                        NC(g_nccl.Recv(s0->d_detseed + (size_t)total * 2, (size_t)take * 2, ncclUint64, g, comm[0], s0->stream));
+                    }
+                }
+
+                total += take;
+            }
+
+            NC(g_nccl.GroupEnd());
+        }
+
+        if (s0->d_traj) {       // trajectory records (-D M), merged like src/mmc_cu_host.cu:790-810 and truncated at maxjumpdebug
+            const unsigned int tcap = s0->cfg.c.maxjumpdebug;
+            unsigned long long ttotal = std::min(tcnt[0], tcap), tall = tcnt[0];
+            NC(g_nccl.GroupStart());
+
+            for (int g = 1; g < ndev; g++) {
+                tall += tcnt[g];
+                const unsigned int take = (unsigned int)std::min<unsigned long long>(std::min(tcnt[g], tcap), tcap - ttotal);
+
+                if (take > 0) {
+                    NC(g_nccl.Send(sess[g]->d_traj, (size_t)take * MMCB_DEBUG_REC, ncclFloat, 0, comm[g], sess[g]->stream));
+                    NC(g_nccl.Recv(s0->d_traj + (size_t)ttotal * MMCB_DEBUG_REC, (size_t)take * MMCB_DEBUG_REC, ncclFloat, g, comm[0], s0->stream));
+                }
+
+                ttotal += take;
+            }
+
+            NC(g_nccl.GroupEnd());
+            const unsigned int t32 = (unsigned int)std::min<unsigned long long>(tall, 0xFFFFFFFFull);
+            CU(cudaSetDevice(devices[0]));
+            CU(cudaMemcpyAsync(s0->d_trajcount, &t32, sizeof(unsigned int), cudaMemcpyHostToDevice, s0->stream));
+        }
+
+        for (int g = 0; g < ndev; g++) {
+            CU(cudaSetDevice(devices[g]));
+            CU(cudaStreamSynchronize(sess[g]->stream));
+        }
+
+        // the first session now holds everything; its detected count is the total that hit a detector (may exceed the capacity)
+        CU(cudaSetDevice(devices[0]));
+        const unsigned int alldet = (unsigned int)std::min<unsigned long long>(detected_all, 0xFFFFFFFFull);
+        CU(cudaMemcpy(s0->d_detcount, &alldet, sizeof(unsigned int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(s0->d_raytet, &raytet, sizeof(double), cudaMemcpyHostToDevice));
+        tr.mark("multi: NCCL reduce + gather");
+        // the fetch normalises with cfg.nphoton in replay mode (Jacobian): the first session was created with the whole count there
+        s0->cfg.c.nphoton = cfg->nphoton;
+        int rc = mmcb_fetch(s0, en.data(), en.data() + MMCB_MAX_SRCNUM, out);
+        out->kernel_ms = *std::max_element(ms.begin(), ms.end());
+        return rc;
+    };
+    const int rc = body();
+    const std::string keep = g_err;
+
+    for (ncclComm_t c : comm) {
+        if (c) {
+            g_nccl.CommDestroy(c);
+        }
+    }
+
+    cleanup();
+
+    if (rc) {
+        g_err = keep;
+    }
+
     return rc;
 }
 
