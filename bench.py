@@ -62,6 +62,13 @@ def workload(name, method=None):
                    tstart=0.0, tend=5e-9, tstep=5e-10, isreflect=1, seed=1648335518, method=method or "elem", basisorder=0,
                    issavedet=1, detpos=[(52.0, 52.0, 90.0, 3.0)], maxdetphoton=3000000)
         desc = "synthetic colin27-scale head (5 tissue ellipsoids on a T5 lattice), detectors + partial paths"
+    elif name == "headatlas":        # configs[3] on the reference's own head mesh (colin27 itself is not shipped): mmclab/example/head_atlas.mat,
+        z = np.load(os.path.join(gold, "head_atlas_mesh.npz"))     # media / source of demo_head_atlas.m:32-38 (tools/make_head_atlas.py)
+        cfg = dict(node=z["node"], elem=z["elem"].astype(np.int32), elemprop=z["etype"].astype(np.int32), prop=z["prop"],
+                   srcpos=tuple(float(v) for v in z["srcpos"]), srcdir=tuple(float(v) for v in z["srcdir"]), tstart=0.0, tend=5e-9, tstep=5e-10,
+                   isreflect=1, seed=1648335518, method=method or "elem", basisorder=0, issavedet=1, issaveexit=1,
+                   detpos=[tuple(float(v) for v in q) for q in z["detpos"]], maxdetphoton=3000000)
+        desc = "mmclab/example/head_atlas.mat (59225 nodes/335713 tets, 5 tissues), pencil at C4h, detectors r=2 mm at 25 and 35 mm + partial paths, 10 gates, RayTracer=%s" % cfg["method"]
     else:
         raise SystemExit("unknown workload " + name)
     return cfg, desc

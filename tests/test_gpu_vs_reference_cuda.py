@@ -195,3 +195,62 @@ def test_replay_outputs_vs_reference_cuda(otype, tmp_path):
             for q in k:
                 print("   ref ", np.round(rd[ok][q], 4), "\n   ours", np.round(gd[i2[ok]][q], 4))
         assert close.mean() > 0.97 and len(np.unique(idx[close])) > 0.99 * close.sum()
+
+
+@needs_refcuda
+def test_head_atlas_detected_photons_and_fluence_vs_reference_cuda_1e8():
+    """BASELINE config C4 on the reference's own head mesh (mmclab/example/head_atlas.mat, 335 713 tets, media and source of
+    demo_head_atlas.m:32-38; tests/golden/head_atlas_mesh.npz by tools/make_head_atlas.py): 1e8 photons, index mismatch, two 2 mm detectors
+    25 and 35 mm from the source saving partial paths and exit positions (-d 1 -x 1).  Against the reference's CUDA kernel on the same GPU:
+    absorbed fraction within 0.1 %, detected-photon count within Poisson noise, mean partial path and scattering count per tissue within
+    1.5 %, per-node CW fluence of every node above 1e-3 of the maximum within 2 %."""
+    from mmc_b200 import mch
+    z = np.load(os.path.join(GOLD, "head_atlas_mesh.npz"))
+    node, elem, et = z["node"], z["elem"].astype(np.int32), z["etype"].astype(np.int32)
+    med = z["prop"][1:]
+    srcpos, srcdir = tuple(float(v) for v in z["srcpos"]), tuple(float(v) for v in z["srcdir"])
+    oriented = mmc.mesh_volumes(node, elem, et)[0]       # the file stores every element inverted; both programs swap nodes 3 and 4 on load
+    e0 = int(mmc.mesh_initelem(node, oriented, srcpos)[0])
+    assert e0 > 0
+    N = 100000000
+    kw = dict(nphoton=N, seed=1648335518, srcpos=srcpos, srcdir=srcdir, tstart=0.0, tend=5e-9, tstep=5e-10, isreflect=1, method=cases.BLBADOUEL,
+              basisorder=1, issavedet=1, issaveexit=1, detpos=[tuple(float(v) for v in q) for q in z["detpos"]], maxdetphoton=3000000)
+    # The reference's CUDA program dies with "an illegal memory access" on this mesh at 1e8 photons as soon as detectors are on
+    # (1e7 photons run, and so do 1e8 without detectors; measured on the B200 box), so its side is split: the fluence run at 1e8 photons
+    # without detectors, the detected-photon statistics from two 1e7-photon runs with different seeds.
+    r = orc.run_ref(node, elem, et, med, cuda=True, timeout=1800, e0=e0, **dict(kw, issavedet=0, issaveexit=0, detpos=None))
+    g = mmc.run(dict(node=node, elem=elem, elemprop=et, prop=z["prop"], method="elem", e0=e0, **{k: v for k, v in kw.items() if k != "method"}))
+    fr, fg = r["absorbed_frac"], g["energyabs"][0] / g["energytot"][0]
+    assert abs(fg - fr) < 1e-3 * fr, (fg, fr)
+    ref = np.where(np.isfinite(r["field_flat"]), r["field_flat"], 0).reshape(10, -1).sum(axis=0)
+    ours = np.where(np.isfinite(g["raw"][..., 0]), g["raw"][..., 0], 0).sum(axis=0)
+    n, med_, p99, worst = _compare(ours, ref)
+    print("head atlas nodal: %d lit nodes, median %.4f, p99 %.4f, worst %.4f; absorbed %.6f vs %.6f; kernel %.0f ms vs reference %.0f ms"
+          % (n, med_, p99, worst, fg, fr, g["kernel_ms"], r.get("kernel_ms", float("nan"))))
+    assert n > 500 and med_ < 0.005 and p99 < 0.015 and worst < 0.02, (n, med_, p99, worst)      # measured: 0.0013 / 0.0069 / 0.0159
+    # detected photons: [detid, nscat[M], ppath[M], p[3], v[3], w0]
+    rows = []
+    for seed in (1648335518, 29012392):
+        rd = orc.run_ref(node, elem, et, med, cuda=True, timeout=900, e0=e0, **dict(kw, nphoton=10000000, seed=seed, maxdetphoton=1000000))
+        rows.append(mch.loadmch(rd["mch"])["detp"])
+    do, dg = np.vstack(rows), g["detp"]
+    scale = 2e7 / N                     # photons behind the reference rows / behind ours
+    no, ng = len(do), len(dg)
+    print("detected: %d of 1e8 photons vs %d of 2e7 (reference)" % (ng, no))
+    assert no > 2000 and abs(no - ng * scale) < 5 * np.sqrt(no + ng * scale * scale), (no, ng)
+    M = len(med)
+    assert do.shape[1] == dg.shape[1] == 2 + 2 * M + 6
+    for m_ in range(1, M):              # tissue 1 (air cavities) does not occur in the mesh
+        for col, what in ((1 + m_, "scattering count"), (1 + M + m_, "partial path")):
+            a, b = dg[:, col].mean(), do[:, col].mean()
+            se = np.sqrt(dg[:, col].var() / ng + do[:, col].var() / no)
+            assert abs(a - b) < 5 * se + 0.015 * abs(b), (what, m_ + 1, a, b, se)
+    assert abs(dg[:, -1].mean() - do[:, -1].mean()) < 1e-6             # launch weight 1
+    ex_o, ex_g = do[:, -7:-4], dg[:, -7:-4]                             # exit positions lie inside the detector sphere
+    dets = np.asarray(kw["detpos"])
+    for rows, ex in ((dg, ex_g), (do, ex_o)):
+        c = dets[rows[:, 0].astype(int) - 1]
+        assert np.all(np.linalg.norm(ex - c[:, :3], axis=1) < c[:, 3] + 1e-3)
+    for k in (1, 2):                    # split between the two detectors
+        a, b = (dg[:, 0] == k).sum() * scale, (do[:, 0] == k).sum()
+        assert abs(a - b) < 5 * np.sqrt(a * scale + b) + 5, (k, a, b)
