@@ -1028,7 +1028,7 @@ struct mmcb_session {
     float4* d_cent = NULL;
     float* d_node = NULL;
     int* d_elem = NULL;
-    int* d_srcelem = NULL;
+    int* d_srcelem = NULL, *d_srccell = NULL, *d_srcitem = NULL;      // candidate elements of wide-field sources and their search grid
     float4* d_med = NULL;
     float* d_pattern = NULL;
     uint32_t* d_seeds = NULL;
@@ -1075,6 +1075,8 @@ static int session_free(mmcb_session* s) {
     dev_free(s->d_node);
     dev_free(s->d_elem);
     dev_free(s->d_srcelem);
+    dev_free(s->d_srccell);
+    dev_free(s->d_srcitem);
     dev_free(s->d_med);
     dev_free(s->d_pattern);
     dev_free(s->d_seeds);
@@ -1251,6 +1253,84 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
 
     if ((rc = dev_alloc_copy(&s->d_srcelem, m.srcelem.data(), m.srcelem.size()))) {
         return rc;
+    }
+
+    // search grid over the candidate elements (see find_launch_elem): about two candidates per cell on average, every candidate entered
+    // in all cells its bounding box (grown by 1e-3, far more than the -1e-4 slack of the enclosure test) touches, in list order
+    int gdim[3] = {0, 0, 0};
+    float glo[3] = {0.f, 0.f, 0.f}, ginv[3] = {0.f, 0.f, 0.f};
+
+    if (m.srcelem.size() > 16 && !getenv("MMCB_NO_SRCGRID")) {
+        const float grow = 1e-3f;
+        float hi[3] = { -VERY_BIG, -VERY_BIG, -VERY_BIG};
+        glo[0] = glo[1] = glo[2] = VERY_BIG;
+        std::vector<float> box(6 * m.srcelem.size());
+
+        for (size_t i = 0; i < m.srcelem.size(); i++) {
+            const int* q = &m.elem[4 * (size_t)(m.srcelem[i] - 1)];
+
+            for (int k = 0; k < 3; k++) {
+                const float c0 = nd(m.node.data(), q[0])[k], c1 = nd(m.node.data(), q[1])[k], c2 = nd(m.node.data(), q[2])[k], c3 = nd(m.node.data(), q[3])[k];
+                box[6 * i + k] = std::min(std::min(c0, c1), std::min(c2, c3)) - grow;
+                box[6 * i + 3 + k] = std::max(std::max(c0, c1), std::max(c2, c3)) + grow;
+                glo[k] = std::min(glo[k], box[6 * i + k]);
+                hi[k] = std::max(hi[k], box[6 * i + 3 + k]);
+            }
+        }
+
+        const double ext[3] = {std::max(hi[0] - glo[0], 1e-6f), std::max(hi[1] - glo[1], 1e-6f), std::max(hi[2] - glo[2], 1e-6f)};
+        const double h = std::cbrt(ext[0] * ext[1] * ext[2] / (0.5 * m.srcelem.size()));
+
+        for (int k = 0; k < 3; k++) {
+            gdim[k] = std::min(256, std::max(1, (int)std::ceil(ext[k] / h)));
+            ginv[k] = (float)(gdim[k] / ext[k]);
+        }
+
+        const size_t ncell = (size_t)gdim[0] * gdim[1] * gdim[2];
+        std::vector<int> count(ncell + 1, 0), item;
+        auto cells = [&](size_t i, int k, int& c0, int& c1) {
+            c0 = std::min(std::max((int)((box[6 * i + k] - glo[k]) * ginv[k]), 0), gdim[k] - 1);
+            c1 = std::min(std::max((int)((box[6 * i + 3 + k] - glo[k]) * ginv[k]), 0), gdim[k] - 1);
+        };
+
+        for (int pass = 0; pass < 2; pass++) {      // count, then fill (candidates in list order within every cell)
+            for (size_t i = 0; i < m.srcelem.size(); i++) {
+                int x0, x1, y0, y1, z0, z1;
+                cells(i, 0, x0, x1);
+                cells(i, 1, y0, y1);
+                cells(i, 2, z0, z1);
+
+                for (int z = z0; z <= z1; z++)
+                    for (int y = y0; y <= y1; y++)
+                        for (int x = x0; x <= x1; x++) {
+                            const size_t c = ((size_t)z * gdim[1] + y) * gdim[0] + x;
+
+                            if (pass == 0) {
+                                count[c + 1]++;
+                            } else {
+                                item[count[c]++] = m.srcelem[i];
+                            }
+                        }
+            }
+
+            if (pass == 0) {
+                for (size_t c = 0; c < ncell; c++) {
+                    count[c + 1] += count[c];
+                }
+
+                item.resize(count[ncell]);
+            } else {                                // the fill advanced every start to its end: shift back
+                for (size_t c = ncell; c > 0; c--) {
+                    count[c] = count[c - 1];
+                }
+
+                count[0] = 0;
+            }
+        }
+
+        if ((rc = dev_alloc_copy(&s->d_srccell, count.data(), count.size())) || (rc = dev_alloc_copy(&s->d_srcitem, item.data(), item.size()))) {
+            return rc;
+        }
     }
 
     {
@@ -1475,6 +1555,9 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     k.slotstride = (unsigned int)(framelen * s->cfg.maxgate);
     k.omega = s->cfg.isrf ? c.omega : 0.f;
     k.isnodalprop = c.nodemua ? (c.nodemusp ? 2 : 1) : 0;
+    memcpy(k.srcgrid_lo, glo, sizeof(glo));
+    memcpy(k.srcgrid_inv, ginv, sizeof(ginv));
+    memcpy(k.srcgrid_dim, gdim, sizeof(gdim));
     mmcb_kargs& a = s->ka;
     memset(&a, 0, sizeof(a));
     a.tet = s->d_tet;
@@ -1483,6 +1566,8 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     a.node = s->d_node;
     a.elem = s->d_elem;
     a.srcelem = s->d_srcelem;
+    a.srccell = s->d_srccell;
+    a.srcitem = s->d_srcitem;
     a.med = s->d_med;
     a.srcpattern = s->d_pattern;
     a.seeds = s->d_seeds;

@@ -98,6 +98,9 @@ struct mmcb_kparam {
     unsigned int slotstride;     // framelen * maxgate: offset between the slots' blocks of the accumulator volume
     float omega;                 // modulation angular frequency (rad/s); > 0 only in the RF kernel variants
     int   isnodalprop;           // 0 off; 1 kargs.eprop[e].x overrides mua; 2 .y overrides mus as well (src/mmc_core.cl:776-793)
+    // launch-element search grid over the candidate elements of wide-field sources (kargs.srccell / kargs.srcitem); dim[0] == 0: none
+    float srcgrid_lo[3], srcgrid_inv[3];
+    int   srcgrid_dim[3];
 };
 
 struct mmcb_kargs {
@@ -107,6 +110,8 @@ struct mmcb_kargs {
     const float*  node;          // nn*3
     const int*    elem;          // ne*4
     const int*    srcelem;
+    const int*    srccell;       // search grid: cell c holds the candidates srcitem[srccell[c] .. srccell[c + 1])
+    const int*    srcitem;       // candidate element ids per cell, in the order of srcelem[]
     const float4* med;           // media table (copied to shared memory by each CTA)
     const float*  srcpattern;
     uint32_t* seeds;             // nthread*4: seed words in, stream states out (same packing)
