@@ -1654,7 +1654,22 @@ static int launchphoton(octx* c, oray* r, uint64_t* ran) {
         ORC_FAIL("source type %d is not restated by the oracle", st);
     }
 
-    if (canfocus && r->focus != 0.f) {
+    if (canfocus && cfg->gpu_semantics && (isnan(r->focus) || (r->focus < 0.f && isinf(r->focus)))) {
+        /* GPU-only launch modes of the wide-field sources (src/mmc_core.cl:1743-1757; the CPU file has neither): focal length NaN = isotropic
+         * directions, -inf = Lambertian (cosine-weighted) about srcdir */
+        float ang = TWO_PI * rand01(ran), sphi = sinf(ang), cphi = cosf(ang), stheta, ctheta;
+
+        if (isnan(r->focus)) {
+            ang = acosf(2.f * rand01(ran) - 1.f);
+            stheta = sinf(ang);
+            ctheta = cosf(ang);
+        } else {
+            stheta = sqrtf(rand01(ran));
+            ctheta = sqrtf(1.f - stheta * stheta);
+        }
+
+        rotatevector(r->vec, stheta, ctheta, sphi, cphi, 1);
+    } else if (canfocus && r->focus != 0.f) {
         float Rn2;
 
         for (k = 0; k < 3; k++) {
