@@ -43,5 +43,22 @@ def build(force=False, verbose=False, extra=(), out=None, tag=""):
     return out or LIB
 
 
+def build_pmmc(force=False):
+    """integration/pmmc/_pmmc*.so: the reference's Python module name and functions (src/pmmc.cpp:1447-1462) on this engine
+    (integration/pmmc_b200.cpp, pybind11, against include/mmc_b200.h only)."""
+    import sysconfig
+    import pybind11
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "integration", "pmmc_b200.cpp")
+    out = os.path.join(root, "integration", "pmmc", "_pmmc" + sysconfig.get_config_var("EXT_SUFFIX"))
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return out
+    cmd = ["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-fvisibility=hidden", "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"],
+           "-I", os.path.join(root, "include"), src, "-o", out, "-L", HERE, "-lmmc_b200", "-Wl,-rpath,$ORIGIN/../../mmc_b200"]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_pmmc(force="--force" in sys.argv))
