@@ -248,9 +248,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])   # strong: --photons is the WHOLE job, split over the ranks (BASELINE C4)
     args = ap.parse_args()
     cfg, desc = workload(args.workload, args.method)
-    nphoton = int(args.photons)
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    total_photons = int(args.photons) * (world_env if args.scaling == "weak" else 1)
+    if args.scaling == "strong":            # reference rule for the split (src/mmc_cu_host.cu:425-429), equal workloads
+        from mmc_b200 import multigpu
+        nphoton = int(multigpu.split_photons(int(args.photons), [1.0] * world_env)[0][int(os.environ.get("RANK", "0"))])
+    else:
+        nphoton = int(args.photons)
     cfg["nphoton"] = nphoton
     if os.environ.get("MMCB_HOTCACHE"):
         cfg["hotcache"] = int(os.environ["MMCB_HOTCACHE"])
@@ -283,6 +290,36 @@ def main():
     field = torch.zeros(dp.fieldlen, dtype=torch.float64 if dp.field_is_double else torch.float32, device=dev)
     sess.set_field_buffer(field.data_ptr())
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    class _DevView:                         # zero-copy torch view of session memory (detected-photon rows, their counter)
+        def __init__(self, ptr, shape, typestr):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+    isdet = bool(cfg.get("issavedet")) and bool(dp.detected)
+    reclen = int(dp.reclen)
+    if isdet:
+        det_rows = torch.as_tensor(_DevView(dp.detected, (int(cfg.get("maxdetphoton", 1000000)), reclen), "<f4"), device=dev)
+        det_count = torch.as_tensor(_DevView(dp.detcount, (1,), "<i4"), device=dev)
+    gathered = {"rows": 0, "prev": 0, "bytes": 0}
+
+    def gather_detected():
+        """north_star's "gather of detector records over NVLink": the rows this step appended on every rank go to rank 0 through NCCL --
+        counts first (all_gather), then the payload padded to the largest count (gather)."""
+        n_now = min(int(det_count.item()), det_rows.shape[0])
+        mine = det_rows[gathered["prev"]:n_now]
+        gathered["prev"] = n_now
+        n = torch.tensor([mine.shape[0]], device=dev, dtype=torch.int64)
+        counts = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(counts, n)
+        counts = [int(c) for c in counts]
+        nmax = max(max(counts), 1)
+        pad = torch.zeros((nmax, reclen), device=dev, dtype=torch.float32)
+        pad[:mine.shape[0]] = mine
+        bufs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, bufs, dst=0)
+        if rank == 0:
+            gathered["rows"] += sum(counts)
+            gathered["bytes"] += sum(counts[1:]) * reclen * 4
     l2pk = l2_peaks(len(cfg["elem"]), dp.fieldlen, local) if rank == 0 else None
 
     # everything of a step (L2 flush, photon kernel, NCCL reduce, timing events) is enqueued on ONE explicit non-default
@@ -308,6 +345,8 @@ def main():
                 dist.reduce(field, dst=0, op=dist.ReduceOp.SUM)
                 if rank != 0:
                     field.zero_()
+                if isdet:
+                    gather_detected()
             e1.record(stream)
             stream.synchronize()
         return e0.elapsed_time(e1), sess.sync()
@@ -315,6 +354,7 @@ def main():
     for i in range(args.warmup):
         step(i, False)
     sess.reset()
+    gathered.update(rows=0, prev=0, bytes=0)
     with torch.cuda.stream(stream):
         field.zero_()
     if dist is not None:
@@ -365,7 +405,7 @@ def main():
         # elem (twice: face-neighbour pass + session table), numbered face neighbours, labels, nodes, seed words; the 96-byte records and
         # the centroids are built on the device.  D2H: the volume + the raw face-neighbour table (numbered on the host)
         h2d = ne * 16 * 2 + ne * 16 + ne * 4 + nn * 12 + 16 * nthread
-        e2e = {"value": world * nphoton * reps / float(tt[0]), "unit": "photons/ms", "h2d_bytes_per_step": int(h2d),
+        e2e = {"value": total_photons * reps / float(tt[0]), "unit": "photons/ms", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(r["raw"].size * 8 + ne * 16), "ms": float(tt[0]) / reps, "kernel_ms": float(np.mean(e2e_kern)), "runs": reps,
                "ms_runs": [round(x, 2) for x in e2e_ms], "warmup_calls": 1}
 
@@ -374,7 +414,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    value = world * nphoton * args.steps / total_ms
+    value = total_photons * args.steps / total_ms
     hbm, peak_src = peaks()
     bps = BYTES_PER_STEP.get(cfg["method"], 92)
     steps_per_launch = raytet / args.steps
@@ -397,13 +437,20 @@ def main():
     gred = (reds * nphoton / (kernel_ms * 1e-3) / 1e9) if reds else None
     fr_atomic = (gred / l2pk["red_gatomics"]) if gred else None
     fr_hbm = achieved / hbm
-    cands = [("l2_gather", fr_gather, l2pk["gather_gsteps"] * bps)] + ([("atomic", fr_atomic, None)] if fr_atomic else []) + [("hbm", fr_hbm, hbm)]
+    # HBM can only bound the kernel when tables + volume do not fit the 126 MB L2 (C3's 640 MB volume); otherwise the algorithmic bytes
+    # never reach DRAM (`traffic`) and the HBM-equivalent figure is kept for reference only
+    working_set = len(cfg["elem"]) * 96 + dp.fieldlen * (8 if dp.field_is_double else 4)
+    spills = working_set > 120e6
+    if spills and traffic:
+        fr_hbm = traffic / (kernel_ms * 1e-3) / 1e9 / hbm
+    cands = [("l2_gather", fr_gather)] + ([("atomic", fr_atomic)] if fr_atomic else []) + ([("hbm", fr_hbm)] if spills else [])
     bound = max(cands, key=lambda c: c[1])[0]
     roof = {"bound": bound, "unit": "GB/s", "traffic": traffic, "kernel_ms": kernel_ms, "gsteps_per_s": gsteps,
             "l2_gather": {"achieved_gsteps_per_s": gsteps, "peak_gsteps_per_s": l2pk["gather_gsteps"], "frac": fr_gather},
             "atomic": {"achieved_gred_per_s": gred, "peak_gred_per_s": l2pk["red_gatomics"], "frac": fr_atomic,
                        "reds_per_photon": reds, "reds_source": ncu.get("report")},
-            "hbm_equivalent": {"achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": fr_hbm, "peak_source": peak_src},
+            "hbm_equivalent": {"achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": peak_src,
+                               "working_set_bytes": int(working_set), "spills_l2": bool(spills)},
             "issue": {"issue_slots_busy": ncu.get("issue_slots_busy"), "ipc": ncu.get("ipc"), "active_threads_per_warp_inst": ncu.get("active_threads"),
                       "source": ncu.get("report")},
             "peak_source": l2pk["source"],
@@ -413,13 +460,13 @@ def main():
     if bound == "atomic":
         roof.update(achieved=gred * 8, peak=l2pk["red_gatomics"] * 8, frac=fr_atomic)
     elif bound == "hbm":
-        roof.update(achieved=achieved, peak=hbm, frac=fr_hbm)
+        roof.update(achieved=fr_hbm * hbm, peak=hbm, frac=fr_hbm)
     else:
         roof.update(achieved=achieved, peak=l2pk["gather_gsteps"] * bps, frac=fr_gather)
     line = {"metric": "photons/ms", "value": value, "unit": "photons/ms", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "photons_per_step_per_gpu": nphoton, "l2": "flushed between timed steps (192 MiB fill)",
+            "config": {"workload": desc, "photons_per_step_per_gpu": nphoton, "photons_per_step": total_photons, "l2": "flushed between timed steps (192 MiB fill)",
                        "accumulator": "f64 red.global.add" if dp.field_is_double else "f32 red.global.add",
                        "raytet_steps_per_photon": steps_per_launch / nphoton, "absorbed_fraction": absorbed,
                        "e2e_warmup_calls": 1, "reference_arm_photons_per_step": int(args.ref_photons),
@@ -428,6 +475,10 @@ def main():
             "gpu_launches": args.steps,
             "clocks": clocks,
             "roofline": roof}
+    if isdet:
+        line["detected"] = {"rows_gathered_on_rank0": gathered["rows"], "per_step": gathered["rows"] / max(1, args.steps),
+                            "nccl_payload_bytes_per_step": gathered["bytes"] / max(1, args.steps), "reclen": reclen,
+                            "how": "single GPU: rows stay in the session" if world == 1 else "counts all_gather + padded gather to rank 0 over NCCL inside every timed step"}
     if e2e is not None:
         line["e2e"] = e2e
 

@@ -24,11 +24,11 @@
 
 // kernel-side launchers (mmcb_kernel.cu)
 extern "C" int mmcb_k_upload_param(const mmcb_kparam* hp, const float* det4, int detnum, cudaStream_t st);
-extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int carveout, int repack,
+extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int carveout, int repack, int iscap,
                                      cudaStream_t st);
 extern "C" int mmcb_k_max_block(int method, int repack);
 extern "C" size_t mmcb_k_rp_smem(int block, int isdet, int devreclen);
-extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int repack, int* blocks_per_sm);
+extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int repack, int iscap, int* blocks_per_sm);
 // mesh pre-processing on the device (mmcb_prep.cu)
 extern "C" int mmcb_k_facenb(const int* d_elem, int ne, int* d_facenb, cudaStream_t st);
 extern "C" int mmcb_k_build_records(const float* d_node, const int* d_elem, const int* d_facenb, const int* d_type, const float* d_med_n, int ne,
@@ -1019,6 +1019,8 @@ struct mmcb_session {
     int grid = 0, block = 128, nthread = 0;
     size_t smem = 0;
     bool isgrid = false, ishp = false, isdet = false, isgeneral = false;
+    float lcap_vox = 4.f;
+    bool iscap = false;            // dual grid: steps longer than kp.lcap are walked in pieces (kernel variant CAP)
     bool repack = false;           // lane re-packing kernel (mmcb_kernel_rp.cuh): two walkers (RNG streams) per thread
     size_t fieldlen = 0, efieldlen = 0;     // output volume / kernel accumulator volume (differ for nodal BLB)
     bool acc_double = true, field_external = false;
@@ -1171,6 +1173,34 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     s->isdet = c.issavedet != 0;
     s->isgeneral = !(c.srctype == MMCB_SRC_PENCIL || c.srctype == MMCB_SRC_ISOTROPIC) || c.srcnum > 1 ||
                    c.seed == MMCB_SEED_FROM_FILE || c.savetraj || c.issaveref || s->cfg.multisrc || s->cfg.isrf || c.nodemua != NULL;
+    // Dual grid: a warp runs the segment loop of a step as long as its longest lane needs.  Where steps span many voxels (skinvessel: 5 um
+    // voxels, 60 um elements: 7.7 of 32 lanes active in the loop) a lane deposits at most 2 * lcap_vox segments per iteration and carries
+    // the rest of the step over (kernel variant CAP, mmcb_kernel.cu).  Where they do not (sphshells, cube60: the typical step is one or
+    // two voxels) the variant would only cost its bookkeeping (+3 % measured), so it is chosen from the typical step length in voxels:
+    // min(mean element edge, longest mean free path) / voxel >= 4.  MMCB_SEGCAP=<voxels> forces it, 0 disables
+    // (profiles/r2c_segcap.jsonl).
+    s->lcap_vox = 4.f;
+
+    if (s->isgrid && !s->cfg.isrf) {
+        double vol = 0, mfp = 0;
+
+        for (int i = 0; i < m.ne; i++) {
+            vol += m.evol[i];
+        }
+
+        for (int i = 1; i <= m.prop; i++) {
+            mfp = std::max(mfp, m.med[i].mus > 1e-6f ? 1.0 / m.med[i].mus : 1e30);
+        }
+
+        const double typical = std::min(std::cbrt(vol / std::max(m.ne, 1)), mfp) / c.steps;
+        s->iscap = typical >= 4.0;
+
+        if (const char* e = getenv("MMCB_SEGCAP")) {
+            s->iscap = atof(e) > 0.0;
+            s->lcap_vox = s->iscap ? (float)atof(e) : 4.f;
+        }
+    }
+
     // EXPERIMENTAL lane re-packing kernel (mmcb_kernel_rp.cuh), opt-in with MMCB_REPACK=1: measured SLOWER than the flattened kernel on
     // every workload (profiles/r2a_repack_*), kept for the record and for its parity test.  It serves every single-pattern source;
     // photon sharing, replay, trajectories, diffuse reflectance, multi-slot sources, RF and per-node optical properties change the
@@ -1481,7 +1511,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     }
 
     int bps = 0;
-    CUK(mmcb_k_occupancy(s->block, s->smem, c.method, s->isdet, s->isgeneral, s->cfg.isrf, s->repack, &bps));
+    CUK(mmcb_k_occupancy(s->block, s->smem, c.method, s->isdet, s->isgeneral, s->cfg.isrf, s->repack, s->iscap, &bps));
 
     if (bps < 1) {
         return fail(MMCB_ERR_CUDA, "kernel cannot be resident with block=%d smem=%zu", s->block, s->smem);
@@ -1534,6 +1564,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     k.framelen = (unsigned int)framelen;
     memcpy(k.nmin, m.nmin, sizeof(k.nmin));
     k.dstep = s->isgrid ? 1.f / c.steps : 1.f;
+    k.segcap = s->iscap ? std::max(2, (int)(2.f * s->lcap_vox)) : 0x7FFFFFFF;
     memcpy(k.crop0, s->cfg.crop0, sizeof(k.crop0));
     k.issavedet = c.issavedet;
     k.ismomentum = c.ismomentum;
@@ -1864,7 +1895,7 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
         ka.trajcount = ka.detcount + 1;
         CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
         CUK(mmcb_k_upload_param(&kp, s->cfg.detpos.data(), c.detnum, st));
-        CUK(mmcb_k_launch_photons(&ka, s->grid, s->block, s->smem_scout, c.method, 0, s->isgeneral, 0, s->carveout, s->repack, st));
+        CUK(mmcb_k_launch_photons(&ka, s->grid, s->block, s->smem_scout, c.method, 0, s->isgeneral, 0, s->carveout, s->repack, s->iscap, st));
         CUK(mmcb_k_hot_select(scr, flen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys, c.hotcache > 0 ? 0.f : MMCB_HOT_MINSHARE, st));
         CU(cudaFreeAsync(scr, st));
         s->hot_ready = true;
@@ -1887,7 +1918,7 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
         kp.hotcache = (part == 1 && s->hot_ready) ? 1 : 0;
         CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
         CUK(mmcb_k_upload_param(&kp, s->cfg.detpos.data(), c.detnum, st));
-        CUK(mmcb_k_launch_photons(&s->ka, s->grid, s->block, kp.hotcache ? s->smem : s->smem_base, c.method, s->isdet, s->isgeneral, s->cfg.isrf, s->carveout, s->repack, st));
+        CUK(mmcb_k_launch_photons(&s->ka, s->grid, s->block, kp.hotcache ? s->smem : s->smem_base, c.method, s->isdet, s->isgeneral, s->cfg.isrf, s->carveout, s->repack, s->iscap, st));
 
         if (part == 0) {     // the streams continue from the states the pilot wrote back (no reseeding)
             CUK(mmcb_k_hot_select(s->d_field, s->efieldlen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys,

@@ -102,6 +102,7 @@ struct Photon {
     unsigned int id;
     int   fixcount;
     unsigned int slotoff;      // multi-slot sources: offset of the photon's slot block in the volume
+    unsigned int kdone;        // dual grid, CAP kernels: segments of the current step that earlier iterations already deposited
     float w_im, oldw_im;       // RF variants: imaginary weight and pending imaginary deposit (src/mmc_core.cl:377,383)
 };
 
@@ -217,6 +218,7 @@ __device__ __forceinline__ void launch_photon(Photon& p, Rng& rng, const mmcb_ka
     p.posidx = 0;
     p.fixcount = 0;
     p.slotoff = 0;
+    p.kdone = 0;
     p.w_im = 0.f;
     p.oldw_im = 0.f;
 
@@ -966,10 +968,11 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
                                  // registers, no spills: cube60 45.5 -> 44.0 ms, sphshells 202 -> 193 ms; 8 CTAs (64 registers) spill and lose;
                                  // Plucker is indifferent; the detector / general-source variants would spill at 72 and keep 5 (profiles/r1l_tune_hp_occupancy.jsonl)
 #endif
-template <int METHOD, bool DET, bool GENERAL, bool RF = false>
+template <int METHOD, bool DET, bool GENERAL, bool RF = false, bool CAP = false>
 __global__ void __launch_bounds__((METHOD <= 1) ? MMCB_MAXTHREADS_HP : MMCB_MAXTHREADS, (METHOD == 1 && !DET && !GENERAL) ? MMCB_MINBLOCKS_HAVEL : ((METHOD <= 1) ? MMCB_MINBLOCKS_HP : MMCB_MINBLOCKS))
 mmcb_photon_kernel(const mmcb_kargs a) {
     static_assert(!RF || (GENERAL && METHOD >= 3), "RF forward runs use the general branch-less Badouel kernels");
+    static_assert(!CAP || (METHOD == 4 && !RF), "long steps are walked in pieces by the dual-grid kernels only");
     constexpr bool GRID = (METHOD == 4);
     constexpr bool HP = (METHOD <= 1);          // Havel / Plucker: 256-byte records, CPU-file semantics (src/mmc_raytrace.c)
     const bool hoton = gp.hotcache != 0 && a.hotstat[MMCB_HOT_STAT_USEFUL] != 0;
@@ -1154,8 +1157,8 @@ mmcb_photon_kernel(const mmcb_kargs a) {
 
         if (state == 1) {
         // ------------------------------------------------------------------ one ray-tetrahedron step
-        nraytet++;
         float Lmove = 0.f, fnx = 0.f, fny = 0.f, fnz = 0.f;
+        bool capped = false;            // dual grid, CAP kernels: the step has segments left for the next iteration (see gp.segcap)
         float4 prop = make_float4(0.f, 0.f, 0.f, 1.f);
         int neweid = 0, type = 0, faceidx = 0;
         unsigned flags = 0;
@@ -1206,6 +1209,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
             Lmove = (pd.x == 0.f) ? R_MIN_MUS : p.slen * pd.x;
             isend = (Lmin > Lmove);
             Lmove = isend ? Lmove : Lmin;
+
             const float rc = pd.y;
             float tnew = p.t + Lmove * rc;
             int gate = (int)((tnew - gp.tstart) * gp.Rtstep);
@@ -1218,6 +1222,9 @@ mmcb_photon_kernel(const mmcb_kargs a) {
             }
 
             float currweight = p.w;
+            // CAP kernels walk the segments of a long step over several iterations (below): the step is recomputed from the untouched
+            // photon every time and committed when its last segment is in
+            const float w_before = p.w, slen_before = p.slen, t_before = p.t;
             float totalloss = __expf(-prop.x * Lmove);
             p.w *= totalloss;
             totalloss = 1.f - totalloss;
@@ -1316,9 +1323,30 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 // atomics.  The loop body is one segment; the run that is still open when the photon leaves the element (or runs
                 // out of time) is closed after the loop.
                 const unsigned int cx = gp.crop0[0], cy = gp.crop0[1];
+                int k0 = 0, k1 = seg;
+
+                if constexpr (CAP) {
+                    // A warp runs this loop as long as its longest lane needs (skinvessel, 5 um voxels: 7.7 of 32 lanes active).  Here a
+                    // lane deposits at most gp.segcap segments per iteration; a step with more of them is NOT committed: the photon keeps
+                    // its pre-step state, remembers how many segments are done (p.kdone) and the next iteration recomputes the same step
+                    // (the warp executes that code for its other lanes anyway) and continues with segment kdone.  The segments, their
+                    // midpoints and weights are exactly the reference's 2 (int(L / voxel) + 1) equal pieces (src/mmc_core.cl:1024-1078).
+                    k0 = (int)p.kdone;
+                    k1 = min(seg, k0 + gp.segcap);
+                    capped = (k1 < seg);
+
+                    if (k0 > 0) {
+                        const float fk = (float)k0;
+                        sx += fk * dx;
+                        sy += fk * dy;
+                        sz += fk * dz;
+                        segw *= __expf(-prop.x * seglen * fk);
+                    }
+                }
+
                 MMCB_UNROLL(MMCB_GRID_UNROLL)
 
-                for (int k = 0; k < seg; k++) {
+                for (int k = k0; k < k1; k++) {
                     const int ix = max(__float2int_rd(sx), 0), iy = max(__float2int_rd(sy), 0), iz = max(__float2int_rd(sz), 0);
                     const unsigned int newidx = (unsigned int)iz * cy + (unsigned int)iy * cx + (unsigned int)ix + tshift;
 
@@ -1353,7 +1381,12 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                     sz += dz;
                 }
 
-                if (flushnow) {
+                if (CAP && capped) {            // more segments to come: the step stays uncommitted
+                    p.kdone = (unsigned int)k1;
+                    p.w = w_before;
+                    p.slen = slen_before;
+                    p.t = t_before;
+                } else if (flushnow) {
                     if (RF ? (p.oldidx != 0xFFFFFFFFu) : (p.oldw > 0.f)) {
                         flush_deposit<GENERAL>(gfield, p.oldidx, p.oldw, p, a, hot);
 
@@ -1367,6 +1400,12 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                     p.oldw_im = 0.f;
                 }
 
+                if constexpr (CAP) {
+                    if (!capped) {
+                        p.kdone = 0;
+                    }
+                }
+
                 if constexpr (RF) {                         // :1209-1212
                     p.w = seg_re;
                     p.w_im = seg_im;
@@ -1378,7 +1417,9 @@ mmcb_photon_kernel(const mmcb_kargs a) {
             hp_step<METHOD, GENERAL>(p, bary0, a, smed, gfield, hot, found, Lmove, isend, timeup, neweid, fnx, fny, fnz, type, flags, prop);
         }
 
-        if (found) {
+        nraytet += (CAP && capped) ? 0u : 1u;
+
+        if (found && !(CAP && capped)) {
             if constexpr (!HP) {
                 p.px += Lmove * p.vx;                       // :1222
                 p.py += Lmove * p.vy;
@@ -1465,7 +1506,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                     }
                 }
             }
-        } else {
+        } else if (!found) {
             // no exit face found: pull the photon towards the centroid and retry (:1932-1935, :2013-2024)
             if ((p.fixcount++ & 0xFF) < MMCB_MAX_TRIAL) {
                 float4 c = a.cent[p.eid - 1];
@@ -1846,7 +1887,15 @@ static photon_kernel_t pick_kernel(int isdet, int isgeneral) {
 
     return isgeneral ? mmcb_photon_kernel<METHOD, false, true> : mmcb_photon_kernel<METHOD, false, false>;
 }
-static photon_kernel_t pick_kernel(int method, int isdet, int isgeneral, int isrf) {
+static photon_kernel_t pick_kernel(int method, int isdet, int isgeneral, int isrf, int iscap = 0) {
+    if (method == 4 && iscap && !isrf) {        // dual grid, long steps walked in pieces (gp.lcap)
+        if (isdet) {
+            return isgeneral ? mmcb_photon_kernel<4, true, true, false, true> : mmcb_photon_kernel<4, true, false, false, true>;
+        }
+
+        return isgeneral ? mmcb_photon_kernel<4, false, true, false, true> : mmcb_photon_kernel<4, false, false, false, true>;
+    }
+
     if (isrf) {         // RF forward: general branch-less Badouel kernels only (mesh or dual-grid deposit)
         if (method == 4) {
             return isdet ? mmcb_photon_kernel<4, true, true, true> : mmcb_photon_kernel<4, false, true, true>;
@@ -1886,8 +1935,8 @@ extern "C" size_t mmcb_k_rp_smem(int block, int isdet, int devreclen) {
 }
 
 extern "C" int mmcb_k_launch_photons(const mmcb_kargs* a, int grid, int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int carveout,
-                                     int repack, cudaStream_t st) {
-    photon_kernel_t k = repack ? pick_kernel_rp(method, isdet) : pick_kernel(method, isdet, isgeneral, isrf);
+                                     int repack, int iscap, cudaStream_t st) {
+    photon_kernel_t k = repack ? pick_kernel_rp(method, isdet) : pick_kernel(method, isdet, isgeneral, isrf, iscap);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 
     if (e != cudaSuccess) {
@@ -1912,8 +1961,8 @@ extern "C" int mmcb_k_max_block(int method, int repack) {      // largest (and d
     return repack ? MMCB_RP_THREADS : ((method <= 1) ? MMCB_MAXTHREADS_HP : MMCB_MAXTHREADS);
 }
 
-extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int repack, int* blocks_per_sm) {
-    photon_kernel_t k = repack ? pick_kernel_rp(method, isdet) : pick_kernel(method, isdet, isgeneral, isrf);
+extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int repack, int iscap, int* blocks_per_sm) {
+    photon_kernel_t k = repack ? pick_kernel_rp(method, isdet) : pick_kernel(method, isdet, isgeneral, isrf, iscap);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 
     if (e == cudaSuccess) {

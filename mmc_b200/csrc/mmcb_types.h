@@ -76,6 +76,7 @@ struct mmcb_kparam {
     unsigned int framelen;       // per-gate stride of the accumulator volume
     // dual grid
     float nmin[3]; float dstep;  // dstep = 1/steps.x
+    int   segcap;                // dual grid, CAP kernels: deposit segments a lane handles per iteration (2 per voxel edge of path)
     unsigned int crop0[3];
     // detection
     int   issavedet, ismomentum, issaveexit, issaveseed, issaveref, detnum, reclen;
