@@ -1469,8 +1469,8 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                         detect = true;
                         exiteid = 0;
                     } else {
-                        p.eid = neweid;
-                    }
+                        p.eid = neweid;     // (pulling the neighbour's record into L1 here -- prefetch.global.L1 in round 1, three LDGSTS.ca copies
+                    }                       // into a shared-memory sink in round 2 -- costs more than it hides: profiles/r2d_negative_results.jsonl)
                 }
             } else {
                 // ---- end of the scattering path: roulette :2101-2114, then a new direction :2117-2135
