@@ -957,6 +957,10 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
 #ifndef MMCB_MINBLOCKS
 #define MMCB_MINBLOCKS 4
 #endif
+#ifndef MMCB_MINBLOCKS_DET
+#define MMCB_MINBLOCKS_DET 3     // BLB kernels with detected-photon records: at 4 CTAs per SM (64 registers) they spill 36 bytes inside the loop (ncu: 2.6e9
+#endif                           // local-memory sectors per 1e7 photons on the head atlas); 3 CTAs (80 registers, no spill): head atlas 325.7 -> 287.8 ms,
+                                 // head-like lattice 288.1 -> 268.8 ms (profiles/r2d_det_occupancy.jsonl)
 #ifndef MMCB_MAXTHREADS_HP
 #define MMCB_MAXTHREADS_HP 128   // Havel / Plucker kernels (83-104 registers)
 #endif
@@ -969,7 +973,7 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
                                  // Plucker is indifferent; the detector / general-source variants would spill at 72 and keep 5 (profiles/r1l_tune_hp_occupancy.jsonl)
 #endif
 template <int METHOD, bool DET, bool GENERAL, bool RF = false, bool CAP = false>
-__global__ void __launch_bounds__((METHOD <= 1) ? MMCB_MAXTHREADS_HP : MMCB_MAXTHREADS, (METHOD == 1 && !DET && !GENERAL) ? MMCB_MINBLOCKS_HAVEL : ((METHOD <= 1) ? MMCB_MINBLOCKS_HP : MMCB_MINBLOCKS))
+__global__ void __launch_bounds__((METHOD <= 1) ? MMCB_MAXTHREADS_HP : MMCB_MAXTHREADS, (METHOD == 1 && !DET && !GENERAL) ? MMCB_MINBLOCKS_HAVEL : ((METHOD <= 1) ? MMCB_MINBLOCKS_HP : (DET ? MMCB_MINBLOCKS_DET : MMCB_MINBLOCKS)))
 mmcb_photon_kernel(const mmcb_kargs a) {
     static_assert(!RF || (GENERAL && METHOD >= 3), "RF forward runs use the general branch-less Badouel kernels");
     static_assert(!CAP || (METHOD == 4 && !RF), "long steps are walked in pieces by the dual-grid kernels only");
