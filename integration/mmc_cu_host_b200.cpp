@@ -194,12 +194,13 @@ extern "C" void mmc_run_cu(mcconfig* cfg, tetmesh* mesh, raytracer* tracer) {
     c.issaveseed = cfg->issaveseed;
     c.isspecular = cfg->isspecular;
     c.issaveref = cfg->issaveref;
-    // mcx_validatecfg coerces -M to a BLB tracer for GPU runs (src/mmc_utils.c:3542-3544); MMC_B200_METHOD restores the
-    // user's choice of Havel/Plucker, which this engine offers on the GPU
+    // mcx_validatecfg coerces -M to a branch-less Badouel tracer for every GPU run (src/mmc_utils.c:3542-3544) before this function sees
+    // cfg->method.  This engine offers Havel and Plucker on the GPU as well; the user's choice comes back in one of two ways:
+    //   * with the one-line host patch of INTEGRATION.md (the coercion is skipped when this stub is linked) cfg->method IS the choice;
+    //   * without any patch, MMC_B200_METHOD=p|h|s|g in the environment overrides the coerced value.
     c.method = cfg->method;
 
-    if (getenv("MMC_B200_METHOD")) {
-        const char* s = getenv("MMC_B200_METHOD");
+    if (const char* s = getenv("MMC_B200_METHOD")) {
         c.method = (s[0] == 'p') ? MMCB_RT_PLUCKER : (s[0] == 'h') ? MMCB_RT_HAVEL : (s[0] == 'g') ? MMCB_RT_BLBADOUEL_GRID : MMCB_RT_BLBADOUEL;
     }
 
@@ -337,7 +338,9 @@ extern "C" void mmc_run_cu(mcconfig* cfg, tetmesh* mesh, raytracer* tracer) {
         out.jacob = cfg->exportjacob;
     }
 
-    MMC_FPRINTF(cfg->flog, "- code name: [MMC-B200] sm_100a photon engine (libmmc_b200 %x)\n", mmcb_version());
+    static const char* tracername[] = {"Plucker", "Havel", "Badouel", "branch-less Badouel", "branch-less Badouel + dual grid"};
+    MMC_FPRINTF(cfg->flog, "- code name: [MMC-B200] sm_100a photon engine (libmmc_b200 %x), tracer: %s\n", mmcb_version(),
+                tracername[(c.method >= 0 && c.method <= 4) ? c.method : 3]);
     {
         std::vector<uint64_t> share(devices.size());
         mmcb_photon_shares((uint64_t)cfg->nphoton, (int)devices.size(), workload.data(), share.data());

@@ -101,6 +101,26 @@ def test_reference_cli_writes_adjoint_jacobians_through_the_b200_engine(tmp_path
 
 @needs_cli
 @pytest.mark.gpu
+@pytest.mark.parametrize("flag", ["h", "p"])
+def test_cli_offers_havel_and_plucker_on_the_gpu(flag):
+    """`-M h` / `-M p` with `-c cuda`: the reference host coerces the tracer to a branch-less Badouel one for every GPU run
+    (mcx_validatecfg, src/mmc_utils.c:3542-3544) before mmc_run_cu sees cfg->method, so the user's choice reaches the stub through
+    MMC_B200_METHOD (or through the one-line host patch of INTEGRATION.md, which makes the variable unnecessary).  Same binary:
+    `-c cuda` runs this engine's Havel / Plucker kernels, `-c sse` the reference's CPU tracers (their only implementation)."""
+    env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1), MMC_B200_METHOD=flag)
+    args = ["--bench", "dmmc-cube60", "-n", "1e6", "-D", "T", "-S", "0", "-M", flag, "-C", "0"]
+    gpu = subprocess.run([CLI] + args + ["-c", "cuda"], capture_output=True, text=True, timeout=600, env=env, cwd="/tmp")
+    assert gpu.returncode == 0, gpu.stdout[-2000:] + gpu.stderr[-2000:]
+    assert "MMC-B200" in gpu.stdout and ("tracer: %s" % {"h": "Havel", "p": "Plucker"}[flag]) in gpu.stdout
+    cpu = subprocess.run([CLI] + args + ["-c", "sse"], capture_output=True, text=True, timeout=600, env=env, cwd="/tmp")
+    assert cpu.returncode == 0, cpu.stdout[-2000:] + cpu.stderr[-2000:]
+    assert abs(_absorbed(gpu.stdout) - _absorbed(cpu.stdout)) < 2.5e-3
+    m = re.search(r"ray-tet (\d+)", gpu.stdout)
+    assert m and abs(int(m.group(1)) / 1e6 - 83.8) < 2.0            # Havel on the 6-tet benchmark mesh: 83.8 tests per photon (BASELINE.md section 3)
+
+
+@needs_cli
+@pytest.mark.gpu
 def test_cli_length_unit_is_applied_once():
     """`-u 0.5`: the reference host multiplies mua/mus by the unit before mmc_run_cu (src/mmc_mesh.c:542-546); the stub must hand the
     engine media that end up scaled ONCE.  Same binary, same command line: `-c cuda` (this engine) against `-c sse` (reference CPU)
