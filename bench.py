@@ -320,7 +320,10 @@ def main():
         if rank == 0:
             gathered["rows"] += sum(counts)
             gathered["bytes"] += sum(counts[1:]) * reclen * 4
-    l2pk = l2_peaks(len(cfg["elem"]), dp.fieldlen, local) if rank == 0 else None
+    # atomic ceiling: random f64 reductions into an L2-RESIDENT volume (at most 54 MB of it): the deposits of a run concentrate around
+    # the beam, so even the 862 MB volume of config C3 is hit where L2 holds it (ncu: DRAM throughput 1 % of peak); uniformly random
+    # reductions over a volume that spills to HBM (23 G/s) would understate the ceiling
+    l2pk = l2_peaks(len(cfg["elem"]), min(dp.fieldlen, 6750000), local) if rank == 0 else None
 
     # everything of a step (L2 flush, photon kernel, NCCL reduce, timing events) is enqueued on ONE explicit non-default
     # stream: torch.cuda.Event only sees the stream it is recorded on, and a NULL stream handle would make the C-ABI fall
