@@ -243,6 +243,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="sphshells")
     ap.add_argument("--method", default=None)
+    ap.add_argument("--basisorder", type=int, default=None)        # 1: nodal output (Havel / Plucker deposit into nodes inside the kernel)
     ap.add_argument("--photons", type=float, default=1e7)
     ap.add_argument("--ref-photons", type=float, default=1e6)      # ~6 s of CPU work per sample at 16 host threads (the reference CPU path runs this workload at 0.15-0.27 k photons/ms)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -251,6 +252,9 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])   # strong: --photons is the WHOLE job, split over the ranks (BASELINE C4)
     args = ap.parse_args()
     cfg, desc = workload(args.workload, args.method)
+    if args.basisorder is not None:
+        cfg["basisorder"] = args.basisorder
+        desc += ", basisorder=%d" % args.basisorder
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
     total_photons = int(args.photons) * (world_env if args.scaling == "weak" else 1)
     if args.scaling == "strong":            # reference rule for the split (src/mmc_cu_host.cu:425-429), equal workloads

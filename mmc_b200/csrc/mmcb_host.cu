@@ -32,6 +32,7 @@ extern "C" size_t mmcb_k_rp_smem(int block, int isdet, int devreclen);
 extern "C" int mmcb_k_occupancy(int block, size_t smem, int method, int isdet, int isgeneral, int isrf, int repack, int iscap, int* blocks_per_sm);
 // mesh pre-processing on the device (mmcb_prep.cu)
 extern "C" int mmcb_k_facenb(const int* d_elem, int ne, int* d_facenb, cudaStream_t st);
+extern "C" int mmcb_k_build_hpaux(const float* d_node, const int* d_elem, const mmcb_tetrec* d_rec, int ne, float* d_aux, cudaStream_t st);
 extern "C" int mmcb_k_build_records(const float* d_node, const int* d_elem, const int* d_facenb, const int* d_type, const float* d_med_n, int ne,
                                     float nout, int isreflect, mmcb_tetrec* d_rec, float4* d_cent, cudaStream_t st);
 // mesh_normalize on the device (mmcb_post.cu)
@@ -890,69 +891,6 @@ void build_records(const PrepMesh& m, const Cfg& cfg, std::vector<mmcb_tetrec>& 
 }
 
 
-// Havel / Plucker tables (tracer_build, src/mmc_mesh.c:1518-1567) -> 256-byte records; neighbours, flags and type as above
-void build_records_big(const PrepMesh& m, const Cfg& cfg, const std::vector<mmcb_tetrec>& small, std::vector<mmcb_tetrec_big>& rec) {
-    static const int PAIRS[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
-    rec.resize(m.ne);
-
-    for (int i = 0; i < m.ne; i++) {
-        mmcb_tetrec_big& r = rec[i];
-        memset(&r, 0, sizeof(r));
-        const int* ee = &m.elem[4 * (size_t)i];
-
-        if (cfg.c.method == MMCB_RT_HAVEL) {
-            for (int j = 0; j < 4; j++) {
-                float* vN = r.tab + 12 * j;
-                const float* a = nd(m.node.data(), ee[OUT[j][0]]), *b = nd(m.node.data(), ee[OUT[j][1]]), *c = nd(m.node.data(), ee[OUT[j][2]]);
-                float AB[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, AC[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
-                float N[3] = {AB[1]* AC[2] - AB[2]* AC[1], AB[2]* AC[0] - AB[0]* AC[2], AB[0]* AC[1] - AB[1]* AC[0]};
-                float E1[3] = {AC[1]* N[2] - AC[2]* N[1], AC[2]* N[0] - AC[0]* N[2], AC[0]* N[1] - AC[1]* N[0]};   // AC x N
-                float E2[3] = {N[1]* AB[2] - N[2]* AB[1], N[2]* AB[0] - N[0]* AB[2], N[0]* AB[1] - N[1]* AB[0]};   // N x AB
-                float Rn2 = 1.f / sqrt(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
-
-                for (int k = 0; k < 3; k++) {
-                    vN[k] = Rn2 * N[k];
-                }
-
-                Rn2 *= Rn2;
-
-                for (int k = 0; k < 3; k++) {
-                    vN[4 + k] = Rn2 * E1[k];
-                    vN[8 + k] = Rn2 * E2[k];
-                }
-
-                vN[3] = vN[0] * a[0] + vN[1] * a[1] + vN[2] * a[2];
-                vN[7] = -(vN[4] * a[0] + vN[5] * a[1] + vN[6] * a[2]);
-                vN[11] = -(vN[8] * a[0] + vN[9] * a[1] + vN[10] * a[2]);
-            }
-        } else {
-            for (int j = 0; j < 6; j++) {       // d = n1 - n0, m = n0 x n1
-                const float* p0 = nd(m.node.data(), ee[PAIRS[j][0]]), *p1 = nd(m.node.data(), ee[PAIRS[j][1]]);
-                r.tab[3 * j] = p1[0] - p0[0];
-                r.tab[3 * j + 1] = p1[1] - p0[1];
-                r.tab[3 * j + 2] = p1[2] - p0[2];
-                r.tab[18 + 3 * j] = p0[1] * p1[2] - p0[2] * p1[1];
-                r.tab[18 + 3 * j + 1] = p0[2] * p1[0] - p0[0] * p1[2];
-                r.tab[18 + 3 * j + 2] = p0[0] * p1[1] - p0[1] * p1[0];
-            }
-
-            for (int j = 0; j < 4; j++) {
-                r.tab[36 + j] = small[i].nx[j];
-                r.tab[40 + j] = small[i].ny[j];
-                r.tab[44 + j] = small[i].nz[j];
-            }
-        }
-
-        for (int j = 0; j < 4; j++) {
-            r.nb[j] = small[i].nb[j];
-            r.node[j] = ee[j];
-        }
-
-        r.type = small[i].type;
-        r.flags = small[i].flags;
-    }
-}
-
 // Device memory comes from the stream-ordered pool (cudaMallocAsync): a session is ~25 buffers, and plain cudaFree costs up
 // to ~20 ms each next to another allocator's arena (measured: 390 ms to tear a session down inside the bench process).
 // The pool keeps the memory for the next session of the process.
@@ -1029,7 +967,7 @@ struct mmcb_session {
     bool acc_double = true, field_external = false;
     // device allocations
     mmcb_tetrec* d_tet = NULL;
-    mmcb_tetrec_big* d_tetbig = NULL;
+    float* d_tetaux = NULL;         // Havel / Plucker nodal output: companion records (mmcb_types.h)
     float4* d_cent = NULL;
     float* d_node = NULL;
     int* d_elem = NULL;
@@ -1067,6 +1005,12 @@ struct mmcb_session {
     uint64_t launched = 0;
 };
 
+// kernel variant bits of mmcb_k_launch_photons / mmcb_k_occupancy: 1 = dual grid with the capped segment loop, 2 = Havel / Plucker
+// with the nodal deposit inside the kernel
+static inline int kvariant(const mmcb_session* s) {
+    return (s->iscap ? 1 : 0) | ((s->ishp && s->cfg.c.basisorder) ? 2 : 0);
+}
+
 static int session_free(mmcb_session* s) {
     if (!s) {
         return 0;
@@ -1075,7 +1019,7 @@ static int session_free(mmcb_session* s) {
     cudaSetDevice(s->device);
     g_stream = s->stream;
     dev_free(s->d_tet);
-    dev_free(s->d_tetbig);
+    dev_free(s->d_tetaux);
     dev_free(s->d_cent);
     dev_free(s->d_node);
     dev_free(s->d_elem);
@@ -1236,7 +1180,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
         return rc;
     }
 
-    if (!s->ishp && !getenv("MMCB_HOST_PREP")) {
+    if (!getenv("MMCB_HOST_PREP")) {
         // branch-less Badouel records and centroids are built on the device (mmcb_prep.cu): 20 bytes per element go up
         // (neighbours + label) instead of 112 (records + centroids)
         int* d_fnb = NULL, *d_type = NULL;
@@ -1270,18 +1214,14 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
             return rc;
         }
 
-        if (s->ishp) {
-            std::vector<mmcb_tetrec_big> big;
-            build_records_big(m, s->cfg, rec, big);
-
-            if ((rc = dev_alloc_copy(&s->d_tetbig, big.data(), big.size()))) {
-                return rc;
-            }
-        }
-
         if ((rc = dev_alloc_copy((float**)&s->d_cent, cent.data(), cent.size()))) {
             return rc;
         }
+    }
+
+    if (s->ishp && c.basisorder) {      // Havel / Plucker nodal deposit: reciprocal node heights + opposite node ids per face
+        CU(cudaMallocAsync(&s->d_tetaux, sizeof(float) * MMCB_HPAUX_FLOATS * (size_t)m.ne, s->stream));
+        CUK(mmcb_k_build_hpaux(s->d_node, s->d_elem, s->d_tet, m.ne, s->d_tetaux, s->stream));
     }
 
     if ((rc = dev_alloc_copy(&s->d_srcelem, m.srcelem.data(), m.srcelem.size()))) {
@@ -1514,7 +1454,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     }
 
     int bps = 0;
-    CUK(mmcb_k_occupancy(s->block, s->smem, c.method, s->isdet, s->isgeneral, s->cfg.isrf, s->repack, s->iscap, &bps));
+    CUK(mmcb_k_occupancy(s->block, s->smem, c.method, s->isdet, s->isgeneral, s->cfg.isrf, s->repack, kvariant(s), &bps));
 
     if (bps < 1) {
         return fail(MMCB_ERR_CUDA, "kernel cannot be resident with block=%d smem=%zu", s->block, s->smem);
@@ -1595,7 +1535,7 @@ static int session_build(mmcb_session* s, const mmcb_config* cfgin, const mmcb_m
     mmcb_kargs& a = s->ka;
     memset(&a, 0, sizeof(a));
     a.tet = s->d_tet;
-    a.tetbig = s->d_tetbig;
+    a.tetaux = s->d_tetaux;
     a.cent = s->d_cent;
     a.node = s->d_node;
     a.elem = s->d_elem;
@@ -1898,7 +1838,7 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
         ka.trajcount = ka.detcount + 1;
         CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
         CUK(mmcb_k_upload_param(&kp, s->cfg.detpos.data(), c.detnum, st));
-        CUK(mmcb_k_launch_photons(&ka, s->grid, s->block, s->smem_scout, c.method, 0, s->isgeneral, 0, s->carveout, s->repack, s->iscap, st));
+        CUK(mmcb_k_launch_photons(&ka, s->grid, s->block, s->smem_scout, c.method, 0, s->isgeneral, 0, s->carveout, s->repack, kvariant(s), st));
         CUK(mmcb_k_hot_select(scr, flen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys, c.hotcache > 0 ? 0.f : MMCB_HOT_MINSHARE, st));
         CU(cudaFreeAsync(scr, st));
         s->hot_ready = true;
@@ -1921,7 +1861,7 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
         kp.hotcache = (part == 1 && s->hot_ready) ? 1 : 0;
         CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
         CUK(mmcb_k_upload_param(&kp, s->cfg.detpos.data(), c.detnum, st));
-        CUK(mmcb_k_launch_photons(&s->ka, s->grid, s->block, kp.hotcache ? s->smem : s->smem_base, c.method, s->isdet, s->isgeneral, s->cfg.isrf, s->carveout, s->repack, s->iscap, st));
+        CUK(mmcb_k_launch_photons(&s->ka, s->grid, s->block, kp.hotcache ? s->smem : s->smem_base, c.method, s->isdet, s->isgeneral, s->cfg.isrf, s->carveout, s->repack, kvariant(s), st));
 
         if (part == 0) {     // the streams continue from the states the pilot wrote back (no reseeding)
             CUK(mmcb_k_hot_select(s->d_field, s->efieldlen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys,

@@ -555,253 +555,96 @@ __device__ __forceinline__ void savedebug(const Photon& p, const mmcb_kargs& a) 
 // ----------------------------------------------------------------------------------------------------
 // Havel and Plucker ray-tetrahedron steps with the semantics of the reference's CPU file, which is their only
 // implementation (src/mmc_raytrace.c:531-800 havel_raytet, :227-508 plucker_raytet):
-// ">=" time-window test, one deposit per step (no run-length merge), barycentric nodal deposit for basisorder=1 with the
-// entry coordinates bary0 carried from element to element by matching global node ids.
+// ">=" time-window test, one deposit per step (no run-length merge), barycentric nodal deposit for basisorder=1.
+//
+// Both tracers run on the 96-byte plane record of the BLB kernels.  The reference keeps per-face edge vectors (Havel, 192 B per
+// element) or per-edge Plucker coordinates (144 B) and gathers them every step; what those tables decide is a statement about
+// the four face planes, and that is how it is evaluated here:
+//   Havel  (havel_sse4, :531-561): first face with n.v >= 0, 0 <= t <= 1e10 and the hit inside the triangle (0 <= u, 0 <= v,
+//          u + v <= 1).  A triangle of a tetrahedron is its plane cut by the three other face planes, so "inside" is
+//          d_j - n_j.(p + t v) >= 0 for the three other faces j -- one FMA each on values the plane tests already produced.  Only
+//          the nearest admissible face can pass (a farther hit lies behind the nearest plane), so it is the one tested.
+//   Plucker (:283-343): the six edge signs say through which face the LINE leaves the element and whether it meets the element
+//          at all; for a convex cell that is: exit face = nearest plane among those with n.v > 0 (negative distances allowed),
+//          and the line meets the cell iff the farthest entry plane (n.v < 0) is not behind it.
+// Exit barycentric coordinates (nodal deposit): the coordinate of node m is the distance to the face opposite m over the node's
+// height above it, so b[opp(j)] = (d_j - n_j.q) * invh_j with invh_j and the node ids in a 32-byte companion record
+// (kargs.tetaux, built on the device, read only by nodal runs).  The same expression at the step's start point replaces the
+// entry coordinates the reference carries from element to element by matching global node ids (:709-720, :456-480): no
+// dependent gather of the neighbour's node ids, no per-photon state.
 // ----------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ld128(const void* p, float (&v)[4]) {
-    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
-}
 __device__ __forceinline__ bool samesign(float a, float b) {     // !((a ^ b) & sign bit), src/mmc_raytrace.c:540-555
     return ((__float_as_uint(a) ^ __float_as_uint(b)) & 0x80000000u) == 0;
 }
-
-
-// barycentric coordinates of the launch point in its element for the nodal Havel/Plucker deposit: cfg->bary0 for point
-// sources (mesh_barycentric on the host), recomputed for area sources like src/mmc_raytrace.c:2613-2640
-__device__ __forceinline__ float4 launch_bary(const Photon& p, const mmcb_kargs& a) {
-    if (gp.basisorder == 0) {
-        return make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-
-    if (!gp.multisrc && (gp.srctype == 0 || (p.eid == gp.e0 && (gp.srctype == 1 || gp.srctype == 2 || gp.srctype == 7)))) {
-        return make_float4(gp.bary0[0], gp.bary0[1], gp.bary0[2], gp.bary0[3]);
-    }
-
-    const int4 e = *(const int4*)(a.elem + 4 * (size_t)(p.eid - 1));
-    const int id[4] = {e.x, e.y, e.z, e.w};
-    float q[4][3];
-    #pragma unroll
-
-    for (int i = 0; i < 4; i++) {
-        q[i][0] = a.node[3 * (size_t)(id[i] - 1)];
-        q[i][1] = a.node[3 * (size_t)(id[i] - 1) + 1];
-        q[i][2] = a.node[3 * (size_t)(id[i] - 1) + 2];
-    }
-
-    const int outn[4][3] = {{0, 3, 1}, {3, 2, 1}, {0, 2, 3}, {0, 1, 2}}, fmap[4] = {2, 0, 1, 3};
-    float b[4], s = 0.f;
-    #pragma unroll
-
-    for (int i = 0; i < 4; i++) {
-        const float* na = q[outn[i][0]], *nb = q[outn[i][1]], *nc = q[outn[i][2]];
-        float abx = nb[0] - na[0], aby = nb[1] - na[1], abz = nb[2] - na[2];
-        float acx = nc[0] - na[0], acy = nc[1] - na[1], acz = nc[2] - na[2];
-        float sx = p.px - na[0], sy = p.py - na[1], sz = p.pz - na[2];
-        b[fmap[i]] = -(sx * (aby * acz - abz * acy) + sy * (abz * acx - abx * acz) + sz * (abx * acy - aby * acx));
-    }
-
-    s = b[0] + b[1] + b[2] + b[3];
-    return make_float4(b[0] / s, b[1] / s, b[2] / s, b[3] / s);
+__device__ __forceinline__ bool signclear(float a) {
+    return (__float_as_uint(a) & 0x80000000u) == 0;
 }
 
-template <int METHOD, bool GENERAL>
-__device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kargs& a, const float4* smed, unsigned long long gfield, const uint2 hot,
+template <int METHOD, bool GENERAL, bool NODAL>
+__device__ __forceinline__ void hp_step(Photon& p, const mmcb_kargs& a, const float4* smed, unsigned long long gfield, const uint2 hot,
                                         bool& found, float& Lmove, bool& isend, bool& timeup, int& neweid, float& fnx, float& fny, float& fnz,
                                         int& type, unsigned& flags, float4& prop) {
-    const mmcb_tetrec_big* rec = a.tetbig + (p.eid - 1);
-    float tail[8];              // nb[4] node[4]
-    int2 tf;
-    float r0[8], r1[8];         // Havel: face planes from the 96-byte record (same normals and offsets as tab[12 i .. 12 i + 3])
+    const mmcb_tetrec* rec = a.tet + (p.eid - 1);
+    constexpr bool nodal = NODAL;       // gp.basisorder != 0 (kernel variant: the element-wise kernels carry no plane values past the face search)
+    float r0[8], r1[8], r2[8];          // nx[4] ny[4] | nz[4] d[4] | nb[4] type flags
+    float ax[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // invh[4], node id opposite face j [4]
+    ld256(rec, r0);
+    ld256((const char*)rec + 32, r1);
+    ld256((const char*)rec + 64, r2);
 
-    if constexpr (METHOD == 1) {
-        // the plane tests, neighbours, label and flags come from the compact record the BLB kernels use (3 x 256-bit, 13 MB for
-        // cube60 instead of 34 MB of 256-byte records); the big record supplies only the edge vectors of ONE face and, for nodal
-        // output, the node ids
-        const mmcb_tetrec* srec = a.tet + (p.eid - 1);
-        float r2[8];
-        ld256(srec, r0);
-        ld256((const char*)srec + 32, r1);
-        ld256((const char*)srec + 64, r2);
-        tail[0] = r2[0];
-        tail[1] = r2[1];
-        tail[2] = r2[2];
-        tail[3] = r2[3];
-        tf = make_int2(__float_as_int(r2[4]), __float_as_int(r2[5]));
-        tail[4] = tail[5] = tail[6] = tail[7] = 0.f;
-
-        if (gp.basisorder) {
-            float nd4[4];
-            ld128(rec->node, nd4);
-            tail[4] = nd4[0];
-            tail[5] = nd4[1];
-            tail[6] = nd4[2];
-            tail[7] = nd4[3];
-        }
-    } else {
-        // Plucker: the edge tables decide the exit face and give its barycentric coordinates; the exit point itself is taken on
-        // that face's plane (compact record), which is the same point as the reference's node interpolation (getinterp, :165-169)
-        // up to rounding and needs no second, dependent round trip for three node positions
-        const mmcb_tetrec* srec = a.tet + (p.eid - 1);
-        ld256(srec, r0);
-        ld256((const char*)srec + 32, r1);
-        ld256(rec->nb, tail);
-        tf = *(const int2*)&rec->type;
+    if (nodal) {
+        ld256(a.tetaux + 8 * (size_t)(p.eid - 1), ax);
     }
 
-    type = tf.x;
+    type = __float_as_int(r2[4]);
+    float S[4], Tn[4], T[4];            // n_j.v, d_j - n_j.p (distance to the plane, inward positive), their ratio
+    #pragma unroll
+
+    for (int j = 0; j < 4; j++) {
+        S[j] = r0[j] * p.vx + r0[4 + j] * p.vy + r1[j] * p.vz;
+        Tn[j] = (-r0[j] * p.px + -r0[4 + j] * p.py) + (-r1[j] * p.pz + r1[4 + j]);
+        T[j] = __fdividef(Tn[j], S[j]);
+    }
+
     int fi = -1;                // tracer face 0..3
-    float Lp0 = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
-    float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;      // barycentric coordinates of the exit point (local node order)
+    float Lp0 = 0.f;
 
     if constexpr (METHOD == 1) {
-        // ---- Havel: first face (in order) with det >= 0, 0 <= t <= 1e10, and the hit inside the triangle (havel_sse4, :531-561).
-        // For a ray that starts inside the element exactly one face passes all three tests, and it is the one with the smallest t.
-        // So: the four plane tests first (4 loads), the two edge tests for the nearest face only (2 loads); the sequential search of
-        // the reference (12 loads) runs only when that face fails its edge tests (origin on an edge / outside after drift).
-        float tu = 0.f, tv = 0.f;
-        {
-            float tt[4], dets[4], detts[4];
-            #pragma unroll
+        // admissible: det = n.v >= 0 and 0 <= t <= 1e10 (the reference's two sign tests on det and on dett, 1e10 det - dett; NaN fails)
+        float tt[4];
+        #pragma unroll
 
-            for (int i = 0; i < 4; i++) {       // n = (r0[i], r0[4+i], r1[i]), offset r1[4+i]
-                dets[i] = r0[i] * p.vx + r0[4 + i] * p.vy + r1[i] * p.vz;
-                detts[i] = (-r0[i] * p.px + -r0[4 + i] * p.py) + (-r1[i] * p.pz + r1[4 + i]);
-                const bool ok = !(__float_as_uint(dets[i]) & 0x80000000u) && samesign(detts[i], 1e10f * dets[i] - detts[i]);
-                const float t = __fdividef(detts[i], dets[i]);
-                tt[i] = (ok && t == t) ? t : 3.0e38f;
-            }
-
-            const float tmin = fminf(fminf(tt[0], tt[1]), fminf(tt[2], tt[3]));
-
-            if (tmin < 3.0e38f) {
-                const int c = (tt[0] == tmin) ? 0 : ((tt[1] == tmin) ? 1 : ((tt[2] == tmin) ? 2 : 3));
-                const float det = sel4(dets, c), dett = sel4(detts, c);
-                float e1[4], e2[4];
-                ld128(rec->tab + 12 * c + 4, e1);
-                ld128(rec->tab + 12 * c + 8, e2);
-                const float qx = p.px * det + dett * p.vx, qy = p.py * det + dett * p.vy, qz = p.pz * det + dett * p.vz;   // w = det
-                const float detu = (qx * e1[0] + qy * e1[1]) + (qz * e1[2] + det * e1[3]);
-                const float detv = (qx * e2[0] + qy * e2[1]) + (qz * e2[2] + det * e2[3]);
-
-                if (samesign(detu, det - detu) && samesign(detv, det - (detu + detv))) {
-                    const float inv = 1.f / det;
-                    const float t = dett * inv;
-
-                    if (t == t) {
-                        fi = c;
-                        Lp0 = t;
-                        tu = detu * inv;
-                        tv = detv * inv;
-                        fnx = sel4(r0, c);
-                        fny = sel4(r0 + 4, c);
-                        fnz = sel4(r1, c);
-                    }
-                }
-            }
+        for (int j = 0; j < 4; j++) {
+            tt[j] = (S[j] >= 0.f && T[j] >= 0.f && T[j] <= 1e10f) ? T[j] : 3.0e38f;
         }
 
-        if (fi < 0) {       // rare: the reference's sequential search, face by face
-            #pragma unroll 1
+        const float tmin = fminf(fminf(tt[0], tt[1]), fminf(tt[2], tt[3]));
+        bool inside = (tmin < 3.0e38f);
+        #pragma unroll
 
-            for (int i = 0; i < 4 && fi < 0; i++) {
-                float n[4], e1[4], e2[4];
-                ld128(rec->tab + 12 * i, n);
-                const float det = n[0] * p.vx + n[1] * p.vy + n[2] * p.vz;
-
-                if (!(__float_as_uint(det) & 0x80000000u)) {
-                    const float dett = (-n[0] * p.px + -n[1] * p.py) + (-n[2] * p.pz + n[3]);
-
-                    if (samesign(dett, 1e10f * det - dett)) {
-                        ld128(rec->tab + 12 * i + 4, e1);
-                        ld128(rec->tab + 12 * i + 8, e2);
-                        const float qx = p.px * det + dett * p.vx, qy = p.py * det + dett * p.vy, qz = p.pz * det + dett * p.vz;   // w = det
-                        const float detu = (qx * e1[0] + qy * e1[1]) + (qz * e1[2] + det * e1[3]);
-
-                        if (samesign(detu, det - detu)) {
-                            const float detv = (qx * e2[0] + qy * e2[1]) + (qz * e2[2] + det * e2[3]);
-
-                            if (samesign(detv, det - (detu + detv))) {
-                                const float inv = 1.f / det;
-                                const float t = dett * inv;
-
-                                if (t == t) {
-                                    fi = i;
-                                    Lp0 = t;
-                                    tu = detu * inv;
-                                    tv = detv * inv;
-                                    fnx = n[0];
-                                    fny = n[1];
-                                    fnz = n[2];
-                                }
-                            }
-                        }
-                    }
-                }
-            }
+        for (int j = 0; j < 4; j++) {       // the hit face itself (and a face hit at the very same distance: a shared edge) is not a test
+            inside = inside && (tt[j] == tmin || fmaf(-tmin, S[j], Tn[j]) >= 0.f);
         }
 
-        // exit barycentrics: b[out[i][0]] = 1-u-v, b[out[i][1]] = u, b[out[i][2]] = v, b[facemap[i]] = 0 (:696-699)
-        const float w0 = 1.f - tu - tv;
-        b0 = (fi == 1) ? 0.f : w0;
-        b1 = (fi == 2) ? 0.f : ((fi == 3) ? tu : tv);
-        b2 = (fi == 0) ? 0.f : ((fi == 3) ? tv : tu);
-        b3 = (fi == 0) ? tu : ((fi == 1) ? w0 : ((fi == 2) ? tv : 0.f));
+        if (inside) {
+            fi = (tt[0] == tmin) ? 0 : ((tt[1] == tmin) ? 1 : ((tt[2] == tmin) ? 2 : 3));
+            Lp0 = tmin;
+        }
     } else {
-        // ---- Plucker: w_i = v.m_i + (p x (p+v)).d_i for the 6 edges, sign pattern per face (:283-343)
-        const float cx = p.py * (p.pz + p.vz) - p.pz * (p.py + p.vy);
-        const float cy = p.pz * (p.px + p.vx) - p.px * (p.pz + p.vz);
-        const float cz = p.px * (p.py + p.vy) - p.py * (p.px + p.vx);
-        float w[6], dm[36];                  // tab: d[6][3] then m[6][3], fetched as nine 128-bit loads
+        float to[4], ti[4];
         #pragma unroll
 
-        for (int i = 0; i < 9; i++) {
-            float q4[4];
-            ld128(rec->tab + 4 * i, q4);
-            dm[4 * i] = q4[0];
-            dm[4 * i + 1] = q4[1];
-            dm[4 * i + 2] = q4[2];
-            dm[4 * i + 3] = q4[3];
+        for (int j = 0; j < 4; j++) {
+            to[j] = (S[j] > 0.f) ? T[j] : 3.0e38f;
+            ti[j] = (S[j] < 0.f) ? T[j] : -3.0e38f;
         }
 
-        #pragma unroll
+        const float tout = fminf(fminf(to[0], to[1]), fminf(to[2], to[3]));
+        const float tin = fmaxf(fmaxf(ti[0], ti[1]), fmaxf(ti[2], ti[3]));
 
-        for (int i = 0; i < 6; i++) {
-            const float* D = dm + 3 * i, *Mv = dm + 18 + 3 * i;
-            w[i] = (p.vx * Mv[0] + p.vy * Mv[1] + p.vz * Mv[2]) + (cx * D[0] + cy * D[1] + cz * D[2]);
-        }
-
-        // fc = {{0,4,2},{3,5,4},{2,5,1},{1,3,0}}; faces 2 and 3 negate their middle edge first (:299-301)
-        const float fa[4] = {w[0], w[3], w[2], w[1]}, fb[4] = {w[4], w[5], -w[5], -w[3]}, fcc[4] = {w[2], w[4], w[1], w[0]};
-        float wa = 0.f, wb = 0.f, wc = 0.f;
-        #pragma unroll
-
-        for (int i = 0; i < 4; i++) {
-            if (fi < 0 && (__float_as_uint(fa[i]) & __float_as_uint(fb[i]) & (__float_as_uint(fcc[i]) ^ 0x80000000u) & 0x80000000u)) {
-                fi = i;
-                wa = fa[i];
-                wb = fb[i];
-                wc = fcc[i];
-            }
-        }
-
-        if (fi >= 0) {
-            // nc = {{3,0,1},{3,1,2},{2,0,3},{1,0,2}}: b[nc0] = -wa Rv, b[nc1] = -wb Rv, b[nc2] = wc Rv
-            const float Rv = 1.f / (-wa - wb + wc);
-            const float ba = -wa * Rv, bb = -wb * Rv, bc = wc * Rv;
-            b0 = (fi == 0) ? bb : ((fi == 1) ? 0.f : bb);
-            b1 = (fi == 0) ? bc : ((fi == 1) ? bb : ((fi == 2) ? 0.f : ba));
-            b2 = (fi == 0) ? 0.f : ((fi == 1) ? bc : ((fi == 2) ? ba : bc));
-            b3 = (fi == 0) ? ba : ((fi == 1) ? ba : ((fi == 2) ? bc : 0.f));
-            // exit point: p + t v on the plane of face fi, t = (d - N.p) / (N.v); outward normal for reflectray (:2272-2276)
-            fnx = sel4(r0, fi);
-            fny = sel4(r0 + 4, fi);
-            fnz = sel4(r1, fi);
-            const float S = p.vx * fnx + p.vy * fny + p.vz * fnz;
-            const float t = __fdividef(sel4(r1 + 4, fi) - (p.px * fnx + p.py * fny + p.pz * fnz), S);
-            Lp0 = (S > 0.f && t > 0.f) ? t : 0.f;
-            ox = p.px + Lp0 * p.vx;
-            oy = p.py + Lp0 * p.vy;
-            oz = p.pz + Lp0 * p.vz;
+        if (tout < 3.0e38f && tin <= tout) {
+            fi = (to[0] == tout) ? 0 : ((to[1] == tout) ? 1 : ((to[2] == tout) ? 2 : 3));
+            Lp0 = fmaxf(tout, 0.f);     // an origin that drifted past the exit face stays where it is and hops on
         }
     }
 
@@ -811,19 +654,23 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
         return;
     }
 
-    flags = ((unsigned)tf.y) >> fi;
+    fnx = sel4(r0, fi);         // outward normal of the exit face for reflectray (:2272-2276)
+    fny = sel4(r0 + 4, fi);
+    fnz = sel4(r1, fi);
+    flags = __float_as_uint(r2[5]) >> fi;
     prop = smed[2 * type];
+    const float4 pd = smed[2 * type + 1];       // 1/mus (0: none), n/c0, 1/mua (0: mua < EPS), c0/n
     const float mus = prop.y;
-    const float dlen = (mus <= EPS) ? R_MIN_MUS : p.slen / mus;
+    const float dlen = (pd.x == 0.f) ? R_MIN_MUS : p.slen * pd.x;
     isend = (Lp0 > dlen);
     Lmove = isend ? dlen : Lp0;
-    neweid = __float_as_int((fi == 0) ? tail[0] : ((fi == 1) ? tail[1] : ((fi == 2) ? tail[2] : tail[3])));
-    const float rc = prop.w * R_C0;
+    neweid = __float_as_int(sel4(r2, fi));
+    const float rc = pd.y;
 
     // common step tail, src/mmc_raytrace.c:357-388 / :633-664 (">=" window test)
     if ((int)((p.t + Lmove * rc - gp.tstart) * gp.Rtstep) >= (int)((gp.tend - gp.tstart) * gp.Rtstep)) {
         timeup = true;
-        Lmove = (gp.tend - p.t) / rc - 1e-4f;
+        Lmove = (gp.tend - p.t) * pd.w - 1e-4f;
     }
 
     float currweight = p.w;
@@ -844,28 +691,20 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
     }
 
     const bool fluence = (gp.outputtype != 2 && gp.outputtype != 4 && gp.outputtype != 5);
-    const bool nodal = gp.basisorder != 0;
 
     if constexpr (METHOD == 1) {
         if (Lp0 == 0.f) {       // :666-668: early break -- no deposit, no clock advance; the photon hops on
             Lmove = 0.f;
             return;
         }
+    }
 
-        p.px += Lmove * p.vx;
-        p.py += Lmove * p.vy;
-        p.pz += Lmove * p.vz;
-    } else {
-        if (!isend && !timeup) {        // crossing: the hop continues from the interpolated exit point (src/mmc_raytrace.c:1895)
-            p.px = ox;
-            p.py = oy;
-            p.pz = oz;
-        } else {
-            p.px += Lmove * p.vx;
-            p.py += Lmove * p.vy;
-            p.pz += Lmove * p.vz;
-        }
+    // a crossing photon continues from the exit point (Plucker: the interpolated pout, src/mmc_raytrace.c:1895 -- the same point)
+    p.px += Lmove * p.vx;
+    p.py += Lmove * p.vy;
+    p.pz += Lmove * p.vz;
 
+    if constexpr (METHOD == 0) {
         if (nodal && !(Lp0 > EPS)) {    // :430: nodal Plucker skips degenerate steps entirely (the position still advances)
             return;
         }
@@ -875,7 +714,7 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
     p.t += Lmove * rc;
 
     if (fluence) {
-        ww = (prop.x < EPS) ? (currweight * Lmove) : (ww / prop.x);
+        ww = (pd.z == 0.f) ? (currweight * Lmove) : (ww * pd.z);
     }
 
     int gate;
@@ -907,36 +746,17 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
         return;
     }
 
-    // ---- nodal deposit: w/2 (bary_in + bary_end) to the four nodes; bary_end is the exit point or, when the path ends
-    //      inside, the point reached (:709-720,763-780 Havel; :456-480 Plucker)
-    const float ratio = Lmove / Lp0;
-
-    if (isend) {
-        b0 = b0 * ratio + bary0.x * (1.f - ratio);
-        b1 = b1 * ratio + bary0.y * (1.f - ratio);
-        b2 = b2 * ratio + bary0.z * (1.f - ratio);
-        b3 = b3 * ratio + bary0.w * (1.f - ratio);
-    }
-
-    const int n0 = __float_as_int(tail[4]), n1 = __float_as_int(tail[5]), n2 = __float_as_int(tail[6]), n3 = __float_as_int(tail[7]);
-
+    // ---- nodal deposit: w/2 (bary_in + bary_end) to the four nodes; bary_end is the exit point or, when the path ends inside,
+    //      the point reached (:709-720,763-780 Havel; :456-480 Plucker).  In plane distances: bary_in[opp(j)] = Tn_j invh_j and
+    //      bary_end[opp(j)] = (Tn_j - L S_j) invh_j with L = Lmove (path ends inside) or Lp0 (exit point; exactly 0 on the exit face)
     if (METHOD == 1 || prop.x > 0.f || fluence) {
-        const float h = ww * 0.5f;
-        flush_deposit<GENERAL>(gfield, (unsigned int)(n0 - 1) + tshift, (bary0.x + b0) * h, p, a, hot);
-        flush_deposit<GENERAL>(gfield, (unsigned int)(n1 - 1) + tshift, (bary0.y + b1) * h, p, a, hot);
-        flush_deposit<GENERAL>(gfield, (unsigned int)(n2 - 1) + tshift, (bary0.z + b2) * h, p, a, hot);
-        flush_deposit<GENERAL>(gfield, (unsigned int)(n3 - 1) + tshift, (bary0.w + b3) * h, p, a, hot);
-    }
+        const float h = ww * 0.5f, Lb = isend ? Lmove : Lp0;
+        #pragma unroll
 
-    // entry coordinates of the next step: same point, renumbered to the neighbour's node order when the face is crossed
-    if (!isend && neweid > 0) {
-        const int4 nx = *(const int4*)(a.tetbig[neweid - 1].node);
-        bary0.x = ((n0 == nx.x) ? b0 : 0.f) + ((n1 == nx.x) ? b1 : 0.f) + ((n2 == nx.x) ? b2 : 0.f) + ((n3 == nx.x) ? b3 : 0.f);
-        bary0.y = ((n0 == nx.y) ? b0 : 0.f) + ((n1 == nx.y) ? b1 : 0.f) + ((n2 == nx.y) ? b2 : 0.f) + ((n3 == nx.y) ? b3 : 0.f);
-        bary0.z = ((n0 == nx.z) ? b0 : 0.f) + ((n1 == nx.z) ? b1 : 0.f) + ((n2 == nx.z) ? b2 : 0.f) + ((n3 == nx.z) ? b3 : 0.f);
-        bary0.w = ((n0 == nx.w) ? b0 : 0.f) + ((n1 == nx.w) ? b1 : 0.f) + ((n2 == nx.w) ? b2 : 0.f) + ((n3 == nx.w) ? b3 : 0.f);
-    } else if (METHOD == 1 || isend) {
-        bary0 = make_float4(b0, b1, b2, b3);
+        for (int j = 0; j < 4; j++) {
+            const float e = (!isend && j == fi) ? 0.f : fmaf(-Lb, S[j], Tn[j]);
+            flush_deposit<GENERAL>(gfield, (unsigned int)(__float_as_int(ax[4 + j]) - 1) + tshift, (Tn[j] + e) * ax[j] * h, p, a, hot);
+        }
     }
 }
 
@@ -961,20 +781,22 @@ __device__ __forceinline__ void hp_step(Photon& p, float4& bary0, const mmcb_kar
 #define MMCB_MINBLOCKS_DET 3     // BLB kernels with detected-photon records: at 4 CTAs per SM (64 registers) they spill 36 bytes inside the loop (ncu: 2.6e9
 #endif                           // local-memory sectors per 1e7 photons on the head atlas); 3 CTAs (80 registers, no spill): head atlas 325.7 -> 287.8 ms,
                                  // head-like lattice 288.1 -> 268.8 ms (profiles/r2d_det_occupancy.jsonl)
+// Havel / Plucker kernels (plane-record formulation, hp_step): the element-wise plain kernels need 70 registers and, like the BLB
+// kernels, run best at 64 with 4 x 256 threads per SM (measured against 6/7/8 x 128 and 3 x 256, profiles/r2h_hp_planes.jsonl); the
+// nodal, detector and general variants (79-96 registers) keep 2 CTAs of 256.
 #ifndef MMCB_MAXTHREADS_HP
-#define MMCB_MAXTHREADS_HP 128   // Havel / Plucker kernels (83-104 registers)
+#define MMCB_MAXTHREADS_HP 256
 #endif
 #ifndef MMCB_MINBLOCKS_HP
-#define MMCB_MINBLOCKS_HP 5      // measured: 4 -> 5 CTAs per SM +2 % (cube60) .. +8 % (sphshells), profiles/r1j_tune_hp_occupancy.jsonl
+#define MMCB_MINBLOCKS_HP 2
 #endif
 #ifndef MMCB_MINBLOCKS_HAVEL
-#define MMCB_MINBLOCKS_HAVEL 7   // the Havel kernel is latency-bound (65 % issue slots busy, two dependent gathers per step): 7 CTAs per SM at 72
-                                 // registers, no spills: cube60 45.5 -> 44.0 ms, sphshells 202 -> 193 ms; 8 CTAs (64 registers) spill and lose;
-                                 // Plucker is indifferent; the detector / general-source variants would spill at 72 and keep 5 (profiles/r1l_tune_hp_occupancy.jsonl)
+#define MMCB_MINBLOCKS_HAVEL 4   // element-wise Havel and Plucker without detector records or general sources
 #endif
-template <int METHOD, bool DET, bool GENERAL, bool RF = false, bool CAP = false>
-__global__ void __launch_bounds__((METHOD <= 1) ? MMCB_MAXTHREADS_HP : MMCB_MAXTHREADS, (METHOD == 1 && !DET && !GENERAL) ? MMCB_MINBLOCKS_HAVEL : ((METHOD <= 1) ? MMCB_MINBLOCKS_HP : (DET ? MMCB_MINBLOCKS_DET : MMCB_MINBLOCKS)))
+template <int METHOD, bool DET, bool GENERAL, bool RF = false, bool CAP = false, bool NODAL = false>
+__global__ void __launch_bounds__((METHOD <= 1) ? MMCB_MAXTHREADS_HP : MMCB_MAXTHREADS, (METHOD <= 1 && !DET && !GENERAL && !NODAL) ? MMCB_MINBLOCKS_HAVEL : ((METHOD <= 1) ? MMCB_MINBLOCKS_HP : (DET ? MMCB_MINBLOCKS_DET : MMCB_MINBLOCKS)))
 mmcb_photon_kernel(const mmcb_kargs a) {
+    static_assert(!NODAL || METHOD <= 1, "nodal deposit inside the kernel: Havel / Plucker only (the BLB kernels spread elements to nodes afterwards)");
     static_assert(!RF || (GENERAL && METHOD >= 3), "RF forward runs use the general branch-less Badouel kernels");
     static_assert(!CAP || (METHOD == 4 && !RF), "long steps are walked in pieces by the dual-grid kernels only");
     constexpr bool GRID = (METHOD == 4);
@@ -1019,7 +841,6 @@ mmcb_photon_kernel(const mmcb_kargs a) {
     Photon p;
     p.eid = 0;
     p.w = 0.f;
-    float4 bary0 = make_float4(0.f, 0.f, 0.f, 0.f);     // HP nodal deposit: barycentric coordinates of the step's start point
     int state = 0;                    // 0: needs a photon, 1: in flight, 2: no photons left
     float etot = 0.f, eesc = 0.f;     // per-thread tallies like src/mmc_core.cl:1908,2155
     unsigned int nraytet = 0;
@@ -1116,10 +937,6 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                         }
 
                         launch_photon<GENERAL>(p, rng, a);
-
-                        if constexpr (HP) {
-                            bary0 = launch_bary(p, a);
-                        }
 
                         if (DET) {
                             if (!GENERAL || gp.srctype != 5 || gp.srcnum == 1) {
@@ -1418,7 +1235,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
 
         }   // found
         } else {
-            hp_step<METHOD, GENERAL>(p, bary0, a, smed, gfield, hot, found, Lmove, isend, timeup, neweid, fnx, fny, fnz, type, flags, prop);
+            hp_step<METHOD, GENERAL, NODAL>(p, a, smed, gfield, hot, found, Lmove, isend, timeup, neweid, fnx, fny, fnz, type, flags, prop);
         }
 
         nraytet += (CAP && capped) ? 0u : 1u;
@@ -1891,7 +1708,22 @@ static photon_kernel_t pick_kernel(int isdet, int isgeneral) {
 
     return isgeneral ? mmcb_photon_kernel<METHOD, false, true> : mmcb_photon_kernel<METHOD, false, false>;
 }
-static photon_kernel_t pick_kernel(int method, int isdet, int isgeneral, int isrf, int iscap = 0) {
+template <int METHOD>
+static photon_kernel_t pick_kernel_nodal(int isdet, int isgeneral) {
+    if (isdet) {
+        return isgeneral ? mmcb_photon_kernel<METHOD, true, true, false, false, true> : mmcb_photon_kernel<METHOD, true, false, false, false, true>;
+    }
+
+    return isgeneral ? mmcb_photon_kernel<METHOD, false, true, false, false, true> : mmcb_photon_kernel<METHOD, false, false, false, false, true>;
+}
+// variant: bit 0 = dual grid with capped segment loop (CAP), bit 1 = Havel / Plucker with nodal deposit (NODAL)
+static photon_kernel_t pick_kernel(int method, int isdet, int isgeneral, int isrf, int variant = 0) {
+    const int iscap = variant & 1;
+
+    if (method <= 1 && (variant & 2)) {
+        return method == 1 ? pick_kernel_nodal<1>(isdet, isgeneral) : pick_kernel_nodal<0>(isdet, isgeneral);
+    }
+
     if (method == 4 && iscap && !isrf) {        // dual grid, long steps walked in pieces (gp.lcap)
         if (isdet) {
             return isgeneral ? mmcb_photon_kernel<4, true, true, false, true> : mmcb_photon_kernel<4, true, false, false, true>;

@@ -173,6 +173,30 @@ __global__ void mmcb_build_records_kernel(const float* __restrict__ node, const 
     }
 }
 
+// Companion record of the Havel / Plucker kernels for nodal output (mmcb_types.h): for tracer face j the node opposite to it is
+// local node {2,0,1,3}[j] (facemap, src/mmc_raytrace.c:60); its height above the face is d_j - n_j.x with the plane of the record.
+__global__ void mmcb_build_hpaux_kernel(const float* __restrict__ node, const int* __restrict__ elem, const mmcb_tetrec* __restrict__ rec, int ne,
+                                        float* __restrict__ aux) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ne; i += gridDim.x * blockDim.x) {
+        const int4 e4 = *(const int4*)(elem + 4 * (size_t)i);
+        const int opp[4] = {e4.z, e4.x, e4.y, e4.w};
+        const mmcb_tetrec r = rec[i];
+        float4 invh;
+        float* o = &invh.x;
+        #pragma unroll
+
+        for (int j = 0; j < 4; j++) {
+            const float* x = node + 3 * (size_t)(opp[j] - 1);
+            const float h = r.d[j] - (r.nx[j] * x[0] + r.ny[j] * x[1] + r.nz[j] * x[2]);
+            o[j] = (h != 0.f) ? __fdiv_rn(1.f, h) : 0.f;
+        }
+
+        float4* out = (float4*)(aux + MMCB_HPAUX_FLOATS * (size_t)i);
+        out[0] = invh;
+        out[1] = make_float4(__int_as_float(opp[0]), __int_as_float(opp[1]), __int_as_float(opp[2]), __int_as_float(opp[3]));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------------------
@@ -226,5 +250,10 @@ extern "C" int mmcb_k_facenb(const int* d_elem, int ne, int* d_facenb, cudaStrea
 extern "C" int mmcb_k_build_records(const float* d_node, const int* d_elem, const int* d_facenb, const int* d_type, const float* d_med_n, int ne,
                                     float nout, int isreflect, mmcb_tetrec* d_rec, float4* d_cent, cudaStream_t st) {
     mmcb_build_records_kernel<<<grid_for((size_t)ne), 256, 0, st>>>(d_node, d_elem, d_facenb, d_type, d_med_n, ne, nout, isreflect, d_rec, d_cent);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int mmcb_k_build_hpaux(const float* d_node, const int* d_elem, const mmcb_tetrec* d_rec, int ne, float* d_aux, cudaStream_t st) {
+    mmcb_build_hpaux_kernel<<<grid_for((size_t)ne), 256, 0, st>>>(d_node, d_elem, d_rec, ne, d_aux);
     return (int)cudaGetLastError();
 }

@@ -45,17 +45,10 @@ struct __attribute__((aligned(32))) mmcb_tetrec {
 #define MMCB_F_TO_VOID(j)  (1u << (4 + (j)))  // this tet has type>0, the neighbour has type 0 (src/mmc_core.cl:1981)
 #define MMCB_F_FROM_VOID(j) (1u << (8 + (j))) // this tet has type 0, the neighbour type>0 (src/mmc_core.cl:1970)
 
-// Havel / Plucker tetrahedron record (256 bytes): the per-face / per-edge tables of tracer_build
-// (src/mmc_mesh.c:1518-1567) followed by neighbours, node ids, type and flags.
-struct __attribute__((aligned(32))) mmcb_tetrec_big {
-    float tab[48];        // Havel: 4 faces x {n^(4), e1(4), e2(4)} (tracer_build, src/mmc_mesh.c:1532-1567);
-                          // Plucker: d[6][3], m[6][3] (:1518-1531) then the BLB face normals nx[4] ny[4] nz[4] for reflectray
-    int   nb[4];          // facenb permuted to tracer face order
-    int   node[4];        // element node ids (1-based)
-    int   type;
-    unsigned int flags;
-    int   pad[6];
-};
+// Havel / Plucker kernels, nodal output only: 32-byte companion of the plane record, per tracer face j the reciprocal height of the
+// opposite node above the face (a barycentric coordinate is a plane distance times this) and that node's 1-based id as int bits:
+//   float invh[4]; int oppnode[4];       (mmcb_build_hpaux_kernel, mmcb_prep.cu)
+#define MMCB_HPAUX_FLOATS 8
 
 struct mmcb_kparam {
     // source
@@ -106,7 +99,7 @@ struct mmcb_kparam {
 
 struct mmcb_kargs {
     const mmcb_tetrec* tet;
-    const mmcb_tetrec_big* tetbig;
+    const float*  tetaux;        // [ne][MMCB_HPAUX_FLOATS], Havel / Plucker with basisorder = 1, else NULL
     const float4* cent;          // element centroids (fixphoton, src/mmc_core.cl:1390-1402)
     const float*  node;          // nn*3
     const int*    elem;          // ne*4
