@@ -56,7 +56,7 @@ extern "C" int mmcb_k_spread_nodes(const void* efield, double* nfield, const int
 extern "C" int mmcb_k_acc_to_double(const void* in, double* out, size_t n, cudaStream_t st);
 extern "C" int mmcb_k_acc_is_double(void);
 extern "C" int mmcb_k_hot_select(const void* field, size_t fieldlen, unsigned int* stat, void* cand, unsigned int cap, unsigned int* keys,
-                                 float minshare, cudaStream_t st);
+                                 float minshare, const double* raytet, const unsigned int* alive, float n0, int maxgate, cudaStream_t st);
 extern "C" int mmcb_k_rng(const uint32_t* dseeds, int nstream, int ndraw, float* dout, unsigned long long* dstate, cudaStream_t st);
 
 #define MMCB_MAX_DEVICES_RING 16
@@ -1804,6 +1804,10 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
 
     const bool scout = pilot && s->cfg.maxgate > 1 && s->cfg.nslots == 1 && !getenv("MMCB_NO_SCOUT");
 
+    // count-mode scout: deposits counted per line and set against the estimated cost of the walk (mmcb_hot_floor_kernel).  Forced-on caches
+    // (hotcache > 0: tests, tuning) and the re-packing kernels keep the weight-ranked selection.  MMCB_HOT_BYWEIGHT=1 restores it for A/B runs.
+    const bool countscout = scout && c.hotcache == 0 && !s->repack && !getenv("MMCB_HOT_BYWEIGHT");
+
     if (scout) {            // a few ten thousand photons rank the lines near the source well enough (the selection works on ratios)
         n0 = std::min<uint64_t>(std::max<uint64_t>(nphoton / 256, 16384), 65536);
     }
@@ -1823,6 +1827,7 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
         kp.threadphoton = (int)(n0 / (uint64_t)s->nthread);
         kp.oddphotons = (int)(n0 - (uint64_t)kp.threadphoton * s->nthread);
         kp.hotcache = 0;
+        kp.countmode = countscout ? 1 : 0;
         kp.savetraj = 0;
         kp.issaveref = 0;
         kp.issavedet = 0;
@@ -1838,8 +1843,11 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
         ka.trajcount = ka.detcount + 1;
         CU(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), st));
         CUK(mmcb_k_upload_param(&kp, s->cfg.detpos.data(), c.detnum, st));
-        CUK(mmcb_k_launch_photons(&ka, s->grid, s->block, s->smem_scout, c.method, 0, s->isgeneral, 0, s->carveout, s->repack, kvariant(s), st));
-        CUK(mmcb_k_hot_select(scr, flen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys, c.hotcache > 0 ? 0.f : MMCB_HOT_MINSHARE, st));
+        // count mode lives in the general kernels only (no instruction in the plain ones): the scout of a plain run uses the general
+        // instantiation of the same tracer, which walks a pencil / isotropic source identically
+        CUK(mmcb_k_launch_photons(&ka, s->grid, s->block, s->smem_scout, c.method, 0, countscout ? 1 : s->isgeneral, 0, s->carveout, s->repack, kvariant(s), st));
+        CUK(mmcb_k_hot_select(scr, flen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys, c.hotcache > 0 ? 0.f : MMCB_HOT_MINSHARE,
+                              countscout ? ka.raytet : NULL, countscout ? ka.trajcount : NULL, (float)n0, s->cfg.maxgate, st));
         CU(cudaFreeAsync(scr, st));
         s->hot_ready = true;
         pilot = false;
@@ -1865,7 +1873,7 @@ int mmcb_launch(mmcb_session* s, uint64_t nphoton, uint64_t photon_offset, int s
 
         if (part == 0) {     // the streams continue from the states the pilot wrote back (no reseeding)
             CUK(mmcb_k_hot_select(s->d_field, s->efieldlen, s->d_hotstat, s->d_hotcand, 2 * MMCB_HOT_SLOTS, s->d_hotkeys,
-                                    c.hotcache > 0 ? 0.f : MMCB_HOT_MINSHARE, st));
+                                    c.hotcache > 0 ? 0.f : MMCB_HOT_MINSHARE, NULL, NULL, 0.f, 0, st));
             s->hot_ready = true;
         }
     }
@@ -2165,8 +2173,15 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
         float mx, tot;
         memcpy(&mx, &st[0], 4);
         memcpy(&tot, &st[MMCB_HOT_STAT_TOTAL], 4);
-        fprintf(stderr, "[mmcb] hot-line cache: ready=%d useful=%u candidates=%u hottest line holds %.4f of the pilot weight\n", (int)s->hot_ready,
-                st[MMCB_HOT_STAT_USEFUL], st[1], tot > 0.f ? mx / tot : 0.f);
+        fprintf(stderr, "[mmcb] hot-line cache: ready=%d useful=%u candidates=%u hottest line holds %.4f of the pilot %s\n", (int)s->hot_ready,
+                st[MMCB_HOT_STAT_USEFUL], st[1], tot > 0.f ? mx / tot : 0.f, st[MMCB_HOT_STAT_FLOOR] ? "deposits" : "weight");
+
+        if (st[MMCB_HOT_STAT_FLOOR]) {
+            float fl, se;
+            memcpy(&fl, &st[MMCB_HOT_STAT_FLOOR], 4);
+            memcpy(&se, &st[MMCB_HOT_STAT_STEPS], 4);
+            fprintf(stderr, "[mmcb] count-mode scout: estimated %.0f ray-tet steps per photon, hottest line %.0f deposits, candidate floor %.0f deposits\n", se, mx, fl);
+        }
     }
 
     // ---- the volume: elem -> node spreading, mesh_normalize (src/mmc_mesh.c:2154-2279) and the slot broadcast of the normaliser

@@ -512,6 +512,10 @@ __device__ __forceinline__ void flush_deposit(unsigned long long gfield, unsigne
     w = 1.f;
 #endif
 
+    if (GENERAL && gp.countmode) {  // scout launch: the scratch volume counts deposits (what the L2 serialises per 128-byte line)
+        w = 1.f;
+    }
+
     if (!GENERAL || gp.srcnum == 1) {
         // CTA-private sums for the hottest 128-byte lines (see mmcb_types.h).  hot = {first index, span} of the cached groups: one
         // unsigned compare sends every deposit outside that window (other gates, other regions) straight to the volume
@@ -1373,6 +1377,10 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 savedebug(p, a);
             }
 
+            if (GENERAL && gp.countmode && timeup) {        // scout: photons that outlive its (first-gate) window
+                atom_add_u32(a.trajcount, 1u);
+            }
+
             if (!GENERAL || gp.srcnum == 1) {
                 eesc += RF ? sqrtf(p.w * p.w + p.w_im * p.w_im) : p.w;     // RF: |w| (:2150-2152)
             } else {
@@ -1551,6 +1559,35 @@ __device__ __forceinline__ int hot_cutbin(const unsigned int* __restrict__ hist,
     return cut;
 }
 
+// Count-mode scout (time-resolved single-slot runs): the scratch volume holds the number of deposits per accumulator for n0 photons
+// followed for the first time gate.  The L2 serialises the atomics of one 128-byte line at ~0.7 G/s (1.43 ns each, tools/microbench),
+// so a line that takes c deposits per photon costs the run c * 1.43 ns per photon, in parallel with every other line and with the
+// walk itself.  The walk costs steps_per_photon / R with R <= 85 G ray-tet steps/s on this GPU (BLB element kernel; slower kernels
+// leave more room).  A line can hold the run up only when c * 1.43 ns is comparable to that, so only groups with
+//     c >= max(MMCB_HOT_CMIN, MMCB_HOT_CFRAC * steps_per_photon / (85 * 1.43))
+// become candidates; with none, the cache (and its lookups) stays off.  steps_per_photon of the whole window is extrapolated from
+// the scout: s0 steps per photon in gate 0 and the share f of photons still alive at its end, s0 * (1 + f + ... + f^(gates-1)) --
+// the loss per gate falls with time (survivors sit deeper), so this under-estimates and errs towards caching.
+#ifndef MMCB_HOT_CMIN
+#define MMCB_HOT_CMIN 0.5f
+#endif
+#ifndef MMCB_HOT_CFRAC
+#define MMCB_HOT_CFRAC 0.5f
+#endif
+__global__ void mmcb_hot_floor_kernel(unsigned int* __restrict__ stat, const double* __restrict__ raytet, const unsigned int* __restrict__ alive,
+                                      float n0, int maxgate) {
+    float floorv = 0.f, steps = 0.f;
+
+    if (raytet && n0 > 0.f) {
+        const float s0 = (float)(*raytet) / n0, f = fminf((float)(*alive) / n0, 0.999f);
+        steps = s0 * (1.f - powf(f, (float)maxgate)) / (1.f - f);
+        floorv = n0 * fmaxf(MMCB_HOT_CMIN, MMCB_HOT_CFRAC * steps / (85.f * 1.43f));
+    }
+
+    stat[MMCB_HOT_STAT_FLOOR] = __float_as_uint(floorv);
+    stat[MMCB_HOT_STAT_STEPS] = __float_as_uint(steps);
+}
+
 __global__ void mmcb_hot_max_kernel(const acc_t* __restrict__ field, size_t ngroups, size_t fieldlen, unsigned int* __restrict__ stat) {
     float m = 0.f, tot = 0.f;
 
@@ -1582,11 +1619,12 @@ __global__ void mmcb_hot_hist_kernel(const acc_t* __restrict__ field, size_t ngr
 
     __syncthreads();
     const unsigned int maxbits = stat[0];
+    const float floorv = __uint_as_float(stat[MMCB_HOT_STAT_FLOOR]);
 
     for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < ngroups; g += (size_t)gridDim.x * blockDim.x) {
         float s = hot_group_sum(field, g, fieldlen);
 
-        if (s > 0.f) {
+        if (s > 0.f && s >= floorv) {
             atomicAdd(&h[hot_bin(s, maxbits)], 1u);
         }
     }
@@ -1603,6 +1641,7 @@ __global__ void mmcb_hot_select_kernel(const acc_t* __restrict__ field, size_t n
                                        uint2* __restrict__ cand, unsigned int cap) {
     const unsigned int maxbits = stat[0];
     const int cut = hot_cutbin(stat + 2, cap);
+    const float floorv = __uint_as_float(stat[MMCB_HOT_STAT_FLOOR]);
 
     if (cut < 0 || maxbits == 0) {
         return;
@@ -1611,7 +1650,7 @@ __global__ void mmcb_hot_select_kernel(const acc_t* __restrict__ field, size_t n
     for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < ngroups; g += (size_t)gridDim.x * blockDim.x) {
         float s = hot_group_sum(field, g, fieldlen);
 
-        if (s > 0.f) {
+        if (s > 0.f && s >= floorv) {
             int b = hot_bin(s, maxbits);
 
             if (b <= cut) {
@@ -1661,15 +1700,17 @@ __global__ void mmcb_hot_build_kernel(const uint2* __restrict__ cand, unsigned i
             }
         }
 
-        const bool useful = (n > 0 && lo <= hi && tot > 0.f && mx > minshare * tot);
+        // weight-mode pilots keep the share rule; a count-mode scout has already filtered its candidates by the floor
+        const bool useful = (n > 0 && lo <= hi && tot > 0.f && (stat[MMCB_HOT_STAT_FLOOR] ? true : (mx > minshare * tot)));
         stat[MMCB_HOT_STAT_USEFUL] = useful ? 1u : 0u;
         stat[MMCB_HOT_STAT_LO] = useful ? (lo << MMCB_HOT_GROUP_LOG2) : 0u;             // window of accumulator indices that can hit the cache
         stat[MMCB_HOT_STAT_SPAN] = useful ? ((hi - lo + 1u) << MMCB_HOT_GROUP_LOG2) : 0u;
     }
 }
 
+// raytet / alive / n0 / maxgate: tallies of a count-mode scout (NULL / 0: the volume holds weights, selection by share)
 extern "C" int mmcb_k_hot_select(const void* field, size_t fieldlen, unsigned int* stat, void* cand, unsigned int cap, unsigned int* keys,
-                                 float minshare, cudaStream_t st) {
+                                 float minshare, const double* raytet, const unsigned int* alive, float n0, int maxgate, cudaStream_t st) {
     const size_t ngroups = (fieldlen + MMCB_HOT_GROUP - 1) >> MMCB_HOT_GROUP_LOG2;
     const int grid = (int)std::min<size_t>(148 * 8, (ngroups + 255) / 256);
     cudaError_t e = cudaMemsetAsync(stat, 0, sizeof(unsigned int) * MMCB_HOT_STAT_WORDS, st);
@@ -1678,6 +1719,7 @@ extern "C" int mmcb_k_hot_select(const void* field, size_t fieldlen, unsigned in
         return (int)e;
     }
 
+    mmcb_hot_floor_kernel<<<1, 1, 0, st>>>(stat, raytet, alive, n0, maxgate);
     mmcb_hot_max_kernel<<<grid, 256, 0, st>>>((const acc_t*)field, ngroups, fieldlen, stat);
     mmcb_hot_hist_kernel<<<grid, 256, 0, st>>>((const acc_t*)field, ngroups, fieldlen, stat);
     mmcb_hot_select_kernel<<<grid, 256, 0, st>>>((const acc_t*)field, ngroups, fieldlen, stat, (uint2*)cand, cap);

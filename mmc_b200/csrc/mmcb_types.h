@@ -19,11 +19,13 @@
 #define MMCB_HOT_EMPTY    0xFFFFFFFFu
 // selection scratch (unsigned int words): [0] bits of the largest group sum, [1] candidate count, [2..33] histogram of the
 // exponent distance to the maximum, [34] bits of the total deposited weight (float), [35] 1 when the cache is worth its lookups
-#define MMCB_HOT_STAT_WORDS 38
+#define MMCB_HOT_STAT_WORDS 40
 #define MMCB_HOT_STAT_TOTAL 34
 #define MMCB_HOT_STAT_USEFUL 35
 #define MMCB_HOT_STAT_LO   36     // first accumulator index of the window spanned by the cached groups
 #define MMCB_HOT_STAT_SPAN 37     // its length (0: cache off)
+#define MMCB_HOT_STAT_FLOOR 38    // float bits: smallest group sum that can make a candidate (count-mode scout, see mmcb_hot_floor_kernel)
+#define MMCB_HOT_STAT_STEPS 39    // float bits: the scout's estimate of ray-tet steps per photon over the whole time window (trace output)
 #define MMCB_HOT_HASH(g)  (((g) * 0x9E3779B1u) >> (32 - MMCB_HOT_SLOTS_LOG2))
 
 // One tetrahedron = one 96-byte record, 32-byte aligned: three 256-bit gathers (LDG.E.256) bring everything a
@@ -85,6 +87,7 @@ struct mmcb_kparam {
     int   hotcache;              // 1: kargs.hotkeys holds MMCB_HOT_SLOTS group keys, deposits to those groups go to shared memory
     unsigned int fieldlen;       // accumulator volume entries (guards the flush of the last, partial group)
     float hotshare;              // the cache is used when the hottest line holds more than this share of the deposited weight
+    int   countmode;             // scout launch (general kernels only): deposits count 1 each, photons alive at tend are tallied in kargs.trajcount
     // multi-slot sources (adjoint mode; src/mmc_core.cl:1431-1515) and RF (frequency-domain) forward runs (:872-896,1043-1078)
     int   multisrc;              // 1: photons are launched from kargs.srcdata[] slots
     int   srcid;                 // < 0: every photon picks a slot uniformly (field has one block per slot); > 0: only slot srcid-1
