@@ -104,6 +104,8 @@ struct Photon {
     unsigned int slotoff;      // multi-slot sources: offset of the photon's slot block in the volume
     unsigned int kdone;        // dual grid, CAP kernels: segments of the current step that earlier iterations already deposited
     float w_im, oldw_im;       // RF variants: imaginary weight and pending imaginary deposit (src/mmc_core.cl:377,383)
+    int   oldeid;              // Havel / Plucker nodal deposit: element of the pending run (0: none; oldidx holds its gate / slot offset)
+    float nw[4];               //   and its four node sums, in the order of the companion record (node opposite tracer face j)
 };
 
 // rotatevector, src/mmc_core.cl:1307-1330
@@ -215,6 +217,8 @@ __device__ __forceinline__ void launch_photon(Photon& p, Rng& rng, const mmcb_ka
     p.slen0 = 0.f;
     p.oldidx = 0xFFFFFFFFu;
     p.oldw = 0.f;
+    p.oldeid = 0;
+    p.nw[0] = p.nw[1] = p.nw[2] = p.nw[3] = 0.f;
     p.posidx = 0;
     p.fixcount = 0;
     p.slotoff = 0;
@@ -584,6 +588,27 @@ __device__ __forceinline__ bool signclear(float a) {
     return (__float_as_uint(a) & 0x80000000u) == 0;
 }
 
+// nodal deposit of a closed run: the four node sums of element p.oldeid in gate / slot block p.oldidx (the node ids are re-read from
+// the companion record of that element, an L1/L2 hit)
+template <bool GENERAL>
+__device__ __forceinline__ void flush_nodal(Photon& p, const mmcb_kargs& a, unsigned long long gfield, const uint2 hot) {
+    if (p.oldeid > 0) {
+        const int4 nd = *(const int4*)(a.tetaux + MMCB_HPAUX_FLOATS * (size_t)(p.oldeid - 1) + 4);
+        const int id[4] = {nd.x, nd.y, nd.z, nd.w};
+        #pragma unroll
+
+        for (int j = 0; j < 4; j++) {
+            if (p.nw[j] != 0.f) {
+                flush_deposit<GENERAL>(gfield, (unsigned int)(id[j] - 1) + p.oldidx, p.nw[j], p, a, hot);
+            }
+
+            p.nw[j] = 0.f;
+        }
+    }
+
+    p.oldeid = 0;
+}
+
 template <int METHOD, bool GENERAL, bool NODAL>
 __device__ __forceinline__ void hp_step(Photon& p, const mmcb_kargs& a, const float4* smed, unsigned long long gfield, const uint2 hot,
                                         bool& found, float& Lmove, bool& isend, bool& timeup, int& neweid, float& fnx, float& fny, float& fnz,
@@ -591,14 +616,16 @@ __device__ __forceinline__ void hp_step(Photon& p, const mmcb_kargs& a, const fl
     const mmcb_tetrec* rec = a.tet + (p.eid - 1);
     constexpr bool nodal = NODAL;       // gp.basisorder != 0 (kernel variant: the element-wise kernels carry no plane values past the face search)
     float r0[8], r1[8], r2[8];          // nx[4] ny[4] | nz[4] d[4] | nb[4] type flags
-    float ax[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // invh[4], node id opposite face j [4]
+    float4 ax4 = make_float4(0.f, 0.f, 0.f, 0.f);              // invh[4] (the node ids behind them are read when a run is written out)
     ld256(rec, r0);
     ld256((const char*)rec + 32, r1);
     ld256((const char*)rec + 64, r2);
 
     if (nodal) {
-        ld256(a.tetaux + 8 * (size_t)(p.eid - 1), ax);
+        ax4 = __ldg((const float4*)(a.tetaux + MMCB_HPAUX_FLOATS * (size_t)(p.eid - 1)));
     }
+
+    const float ax[4] = {ax4.x, ax4.y, ax4.z, ax4.w};
 
     type = __float_as_int(r2[4]);
     float S[4], Tn[4], T[4];            // n_j.v, d_j - n_j.p (distance to the plane, inward positive), their ratio
@@ -753,13 +780,21 @@ __device__ __forceinline__ void hp_step(Photon& p, const mmcb_kargs& a, const fl
     // ---- nodal deposit: w/2 (bary_in + bary_end) to the four nodes; bary_end is the exit point or, when the path ends inside,
     //      the point reached (:709-720,763-780 Havel; :456-480 Plucker).  In plane distances: bary_in[opp(j)] = Tn_j invh_j and
     //      bary_end[opp(j)] = (Tn_j - L S_j) invh_j with L = Lmove (path ends inside) or Lp0 (exit point; exactly 0 on the exit face)
+    //      The reference adds the four shares every step (:713-720, :470-480); steps that stay in one element and gate are summed in
+    //      registers first and written when the photon leaves the element, changes gate or ends (same totals, fewer atomics).
     if (METHOD == 1 || prop.x > 0.f || fluence) {
+        if (p.eid != p.oldeid || tshift != p.oldidx) {
+            flush_nodal<GENERAL>(p, a, gfield, hot);
+            p.oldeid = p.eid;
+            p.oldidx = tshift;
+        }
+
         const float h = ww * 0.5f, Lb = isend ? Lmove : Lp0;
         #pragma unroll
 
         for (int j = 0; j < 4; j++) {
             const float e = (!isend && j == fi) ? 0.f : fmaf(-Lb, S[j], Tn[j]);
-            flush_deposit<GENERAL>(gfield, (unsigned int)(__float_as_int(ax[4 + j]) - 1) + tshift, (Tn[j] + e) * ax[j] * h, p, a, hot);
+            p.nw[j] += (Tn[j] + e) * ax[j] * h;
         }
     }
 }
@@ -787,7 +822,7 @@ __device__ __forceinline__ void hp_step(Photon& p, const mmcb_kargs& a, const fl
                                  // head-like lattice 288.1 -> 268.8 ms (profiles/r2d_det_occupancy.jsonl)
 // Havel / Plucker kernels (plane-record formulation, hp_step): the element-wise plain kernels need 70 registers and, like the BLB
 // kernels, run best at 64 with 4 x 256 threads per SM (measured against 6/7/8 x 128 and 3 x 256, profiles/r2h_hp_planes.jsonl); the
-// nodal, detector and general variants (79-96 registers) keep 2 CTAs of 256.
+// plain nodal kernels run 3 CTAs of 256 (80 registers), the detector and general variants (86-115 registers) 2.
 #ifndef MMCB_MAXTHREADS_HP
 #define MMCB_MAXTHREADS_HP 256
 #endif
@@ -797,8 +832,11 @@ __device__ __forceinline__ void hp_step(Photon& p, const mmcb_kargs& a, const fl
 #ifndef MMCB_MINBLOCKS_HAVEL
 #define MMCB_MINBLOCKS_HAVEL 4   // element-wise Havel and Plucker without detector records or general sources
 #endif
+#ifndef MMCB_MINBLOCKS_HPNODAL
+#define MMCB_MINBLOCKS_HPNODAL 3 // nodal Havel and Plucker, plain: 80 registers without spills (2 CTAs: cube60 72.7 ms, 3: 60.4 ms, 4 with 20-40 B spilled: 64.7 ms)
+#endif
 template <int METHOD, bool DET, bool GENERAL, bool RF = false, bool CAP = false, bool NODAL = false>
-__global__ void __launch_bounds__((METHOD <= 1) ? MMCB_MAXTHREADS_HP : MMCB_MAXTHREADS, (METHOD <= 1 && !DET && !GENERAL && !NODAL) ? MMCB_MINBLOCKS_HAVEL : ((METHOD <= 1) ? MMCB_MINBLOCKS_HP : (DET ? MMCB_MINBLOCKS_DET : MMCB_MINBLOCKS)))
+__global__ void __launch_bounds__((METHOD <= 1) ? MMCB_MAXTHREADS_HP : MMCB_MAXTHREADS, (METHOD <= 1 && !DET && !GENERAL) ? (NODAL ? MMCB_MINBLOCKS_HPNODAL : MMCB_MINBLOCKS_HAVEL) : ((METHOD <= 1) ? MMCB_MINBLOCKS_HP : (DET ? MMCB_MINBLOCKS_DET : MMCB_MINBLOCKS)))
 mmcb_photon_kernel(const mmcb_kargs a) {
     static_assert(!NODAL || METHOD <= 1, "nodal deposit inside the kernel: Havel / Plucker only (the BLB kernels spread elements to nodes afterwards)");
     static_assert(!RF || (GENERAL && METHOD >= 3), "RF forward runs use the general branch-less Badouel kernels");
@@ -1393,7 +1431,9 @@ mmcb_photon_kernel(const mmcb_kargs a) {
             // when the run ended on `isend` -- it flushes on the NEXT step, which never comes; we keep that behaviour.  The
             // Havel/Plucker kernels follow the CPU file, which deposits every step: their pending run is written out.
             if constexpr (HP) {
-                if (p.oldw > 0.f) {
+                if constexpr (NODAL) {
+                    flush_nodal<GENERAL>(p, a, gfield, hot);
+                } else if (p.oldw > 0.f) {
                     flush_deposit<GENERAL>(gfield, p.oldidx, p.oldw, p, a, hot);
                 }
 

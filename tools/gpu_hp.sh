@@ -7,8 +7,8 @@ timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_c1_1e8.py 
 fi
 for v in $VARS; do
   if [ "$v" = product ]; then LIB=mmc_b200/libmmc_b200.so; else LIB=build/variants/libmmc_b200_$v.so; fi
-  for wl in "cube60 havel 0" "cube60 plucker 0" "sphshells havel 0" "sphshells plucker 0" "cube60 havel 1" "cube60 plucker 1"; do
-    set -- $wl
+  for wl in ${WLS:-"cube60:havel:0 cube60:plucker:0 sphshells:havel:0 sphshells:plucker:0 cube60:havel:1 cube60:plucker:1 sphshells:havel:1"}; do
+    set -- ${wl//:/ }
     MMCB_LIB=$PWD/$LIB python bench.py --workload $1 --method $2 --basisorder $3 --no-cpu-baseline --no-e2e --no-ref-cuda --steps 3 --warmup 2 2>/dev/null | python -c "
 import sys,json
 j=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=j['roofline']
