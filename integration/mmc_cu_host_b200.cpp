@@ -102,7 +102,7 @@ extern "C" int mcx_list_cu_gpu(mcconfig* cfg, GPUInfo** info) {     // src/mmc_c
 extern "C" void mmc_run_cu(mcconfig* cfg, tetmesh* mesh, raytracer* tracer) {
     GPUInfo* gpuinfo = NULL;
     unsigned int activedev = 0;
-    (void)tracer;               // the engine builds its own tables (96-/256-byte records) from node/elem
+    (void)tracer;               // the engine builds its own tables (96-byte plane records) from node/elem
 
     if (!(activedev = mcx_list_cu_gpu(cfg, &gpuinfo))) {
         mcx_error(-1, "No GPU device found\n", __FILE__, __LINE__);
