@@ -416,17 +416,8 @@ def run(cfg):
         sz = Sizes()
         _check(L.mmcb_get_sizes(h, C.byref(sz)))
         buf = _OutBuffers(prob, sz)
-        respin = max(1, int(prob.cfg.respin))
-        n, per, ms = int(prob.cfg.nphoton), int(prob.cfg.nphoton) // respin, 0.0
-        t = C.c_float()
-        for it in range(respin):                      # src/mmc_cu_host.cu:656,893-906
-            cnt = per if it < respin - 1 else n - per * (respin - 1)
-            _check(L.mmcb_launch(h, cnt, per * it, int(prob.cfg.seed), it, None))
-            _check(L.mmcb_sync(h))
-            _check(L.mmcb_last_kernel_ms(h, C.byref(t)))
-            ms += t.value
-        _check(L.mmcb_fetch(h, None, None, C.byref(buf.out)))
-        buf.out.kernel_ms = ms
+        # all respins (src/mmc_cu_host.cu:656,893-906) + fetch; the library pre-faults a large result array while the last launch runs
+        _check(L.mmcb_run_session(h, C.byref(buf.out)))
     finally:
         L.mmcb_destroy(h)
     return buf.result(prob)
