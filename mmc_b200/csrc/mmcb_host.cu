@@ -2466,7 +2466,9 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
 // here, eight threads wide, while the GPU works: one read-modify-write of the first byte of every 4 KB page leaves the contents as
 // they are (accumulate mode adds to them later).  Small volumes skip it (measured neutral for 18 MB, profiles/r1l_negative_results.jsonl).
 static void prefault_pages(void* ptr, size_t bytes) {
-    if (!ptr || bytes < ((size_t)64 << 20) || getenv("MMCB_NO_PREFAULT")) {
+    static const size_t minbytes = (size_t)(getenv("MMCB_PREFAULT_MIN_MB") ? atoi(getenv("MMCB_PREFAULT_MIN_MB")) : 64) << 20;
+
+    if (!ptr || bytes < minbytes || getenv("MMCB_NO_PREFAULT")) {
         return;
     }
 

@@ -19,7 +19,29 @@ import orc  # noqa: E402
 from mmc_b200 import meshgen  # noqa: E402
 
 
+def c2(nph):
+    """BASELINE config C2 (the headline workload): shipped dmmc_sphshells mesh, index mismatch + reflection, dual-grid output (61^3 voxels of
+    1 mm), 10 gates, through the reference CPU binary (-M g) -> tests/golden/ref_c2_1e8.npz: CW fluence per voxel as float16 of the value
+    normalised to its maximum where it exceeds 1e-4 of it (the test reads 1e-3 and above), per-gate sums, absorbed fraction.
+    usage: python tools/make_golden_1e8.py c2 [nphoton]"""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "sphshells_mesh.npz"))
+    t0 = time.time()
+    r = orc.run_ref(z["node"], z["elem"], z["etype"], z["prop"], nthread=os.cpu_count() or 1, timeout=4 * 3600, nphoton=nph, seed=1648335518,
+                    srcpos=(30.0, 30.1, 0.0), srcdir=(0, 0, 1), tstart=0.0, tend=5e-9, tstep=5e-10, isreflect=1, method=cases.GRID, basisorder=0,
+                    steps=1.0, e0=4916, evol=z["evol"])
+    f = r["field_flat"].reshape(10, -1)
+    cw = f.sum(axis=0)
+    keep = np.flatnonzero(cw > 1e-4 * cw.max()).astype(np.uint32)
+    meta = dict(nphoton=nph, absorbed_frac=r["absorbed_frac"], raytet=r["raytet"], speed=r.get("speed"), wall_s=time.time() - t0,
+                threads=os.cpu_count(), nvox=int(cw.size), cwmax=float(cw.max()))
+    print("c2", meta, flush=True)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_c2_1e8.npz"), idx=keep, cw=cw[keep].astype(np.float32),
+                        gatesum=f.sum(axis=1), meta=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "c2":
+        return c2(int(float(sys.argv[2])) if len(sys.argv) > 2 else 100000000)
     nph = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100000000
     node, elem, et = meshgen.cube60()
     med = [(0.005, 1.0, 0.01, 1.37)]
