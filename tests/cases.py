@@ -70,6 +70,11 @@ CASES = {
     "planar_havel_nodal": dict(mesh="slab", method=HAVEL, basisorder=1, isreflect=1, srctype=4, srcpos=(5.0, 5.0, -1.0),
                                srcparam1=(10.0, 0, 0, 0), srcparam2=(0, 10.0, 0, 0), exact=False),
     "blb_dref": dict(method=BLBADOUEL, isreflect=1, issaveref=1, exact=True),
+    # detected-photon records from the Havel / Plucker kernels (element-wise and nodal kernel variants with detector columns)
+    "havel_elem_det": dict(method=HAVEL, isreflect=1, issavedet=1, issaveexit=1, ismomentum=1,
+                           detpos=[(10, 8, 0, 1.5), (10, 12, 0, 1.5)], exact=False),
+    "plucker_nodal_det": dict(method=PLUCKER, isreflect=1, basisorder=1, issavedet=1, issaveexit=1,
+                              detpos=[(10, 8, 0, 1.5), (10, 12, 0, 1.5)], exact=True),
 }
 
 

@@ -188,7 +188,7 @@ def test_energy_conservation_and_deposit_completeness(mesh):
     assert abs(g["raw"].sum() / g["energyabs"][0] - 1) < 2e-4
 
 
-HP_CASES = ["havel_elem", "havel_nodal", "plucker_elem", "plucker_nodal", "planar_havel_nodal"]
+HP_CASES = ["havel_elem", "havel_nodal", "plucker_elem", "plucker_nodal", "planar_havel_nodal", "havel_elem_det", "plucker_nodal_det"]
 
 
 @pytest.mark.parametrize("name", HP_CASES)
@@ -217,6 +217,16 @@ def test_havel_plucker_parity_vs_oracle(name):
     rel = np.abs(cw_g[lit] - cw_o[lit]) / cw_o[lit]
     assert np.median(rel) < 0.05, np.median(rel)
     assert np.mean(rel) < 0.08, np.mean(rel)
+    if kw.get("issavedet"):                         # detected-photon records of the detector kernel variants (CPU-file columns)
+        no, ng = o["detectedcount"], len(g["detp"])
+        assert abs(no - ng) < 6 * np.sqrt(max(no, 1)) + 5, (no, ng)
+        assert g["detp"].shape[1] == o["reclen"]
+        do, dg = o["detected"][:no], g["detp"]
+        M = len(med)
+        for col in (1, 1 + M):                      # scattering counts and partial paths of medium 1
+            assert abs(do[:, col].mean() - dg[:, col].mean()) < 0.1 * max(abs(do[:, col].mean()), 0.05)
+        assert abs(do[:, 0].mean() - dg[:, 0].mean()) < 0.1            # detector id mix
+        assert np.allclose(np.linalg.norm(dg[:, -4:-1], axis=1), 1.0, atol=1e-4)
 
 
 def test_three_tracers_agree_on_cube60():
