@@ -2146,6 +2146,10 @@ int mmcb_fetch(mmcb_session* s, const double* energytot, const double* energyesc
     out->detectedcount = s->isdet ? std::min(det, c.maxdetphoton) : 0;   // overflow is a warning, data truncated (src/mmc_cu_host.cu:823-834)
     out->trajcount = std::min(traj, c.maxjumpdebug);
 
+    if (getenv("MMCB_COUNT_FIX")) {     // analysis builds (-DMMCB_COUNT_FIX): see the kernel's not-found path
+        fprintf(stderr, "[mmcb] not-found events %u, photons dropped after %d retries %u\n", traj & 0xFFFFFu, MMCB_MAX_TRIAL, traj >> 20);
+    }
+
     if (out->detected && out->detectedcount) {
         CU(cudaMemcpy(out->detected, s->d_detected, sizeof(float) * (size_t)out->detectedcount * s->cfg.reclen, cudaMemcpyDeviceToHost));
     }

@@ -804,6 +804,9 @@ __device__ __forceinline__ void hp_step(Photon& p, const mmcb_kargs& a, const fl
 // enum TRTMethod, src/mmc_utils.h); DET: detected-photon records;
 // GENERAL: area sources, photon sharing, replay, trajectories, diffuse reflectance.
 // ----------------------------------------------------------------------------------------------------
+#ifndef MMCB_EXP
+#define MMCB_EXP(x) __expf(x)
+#endif
 #ifndef MMCB_GRID_UNROLL
 #define MMCB_GRID_UNROLL 2      // segment loop of the dual-grid deposit (measured: profiles/)
 #endif
@@ -1088,7 +1091,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
             // CAP kernels walk the segments of a long step over several iterations (below): the step is recomputed from the untouched
             // photon every time and committed when its last segment is in
             const float w_before = p.w, slen_before = p.slen, t_before = p.t;
-            float totalloss = __expf(-prop.x * Lmove);
+            float totalloss = MMCB_EXP(-prop.x * Lmove);
             p.w *= totalloss;
             totalloss = 1.f - totalloss;
 
@@ -1166,7 +1169,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
             } else {                                        // dual-grid deposit :1022-1206
                 int seg = ((int)(Lmove * gp.dstep) + 1) << 1;
                 float seglen = Lmove / seg;
-                float segdecay = __expf(-prop.x * seglen);
+                float segdecay = MMCB_EXP(-prop.x * seglen);
                 // segment midpoints in voxel units: g = ((p - nmin) + (k + 1/2) v seglen) / step, index = max(floor(g), 0) like the
                 // reference's `(S.x > 0) ? __float2int_rd(S.x * dstep) : 0` (:1056-1058)
                 const float vs = seglen * gp.dstep;
@@ -1291,7 +1294,9 @@ mmcb_photon_kernel(const mmcb_kargs a) {
 
             // progress guard (not in the reference): a photon that makes no headway for MMCB_MAX_STALL consecutive steps is
             // trapped between degenerate/inverted tetrahedra (the reference CPU path spins forever there) and is dropped
-            p.fixcount = (Lmove > 0.f) ? 0 : (p.fixcount + 0x100);
+            // fixcount: bits 0-7 = consecutive failed searches (the reference's `fixcount`, which it clears at every hop, :2010 -- also at a
+            // zero-length one), bits 8-15 = relocations of this photon (below; never cleared), bits 16+ = consecutive steps without headway
+            p.fixcount = (Lmove > 0.f) ? (p.fixcount & 0xFF00) : ((p.fixcount & ~0xFF) + 0x10000);
 
             if (DET) {                                      // :1943-1945
                 if (type != acct) {
@@ -1302,7 +1307,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                 accL += Lmove;
             }
 
-            if (timeup || p.fixcount >= (MMCB_MAX_STALL << 8)) {
+            if (timeup || p.fixcount >= (MMCB_MAX_STALL << 16)) {
                 terminate = true;                           // :1928-1930 / :2007-2009 (photon stays inside: no detection)
             } else if (!isend) {
                 // ---- cross the face: neighbour hop + boundary physics :1950-1990
@@ -1371,13 +1376,46 @@ mmcb_photon_kernel(const mmcb_kargs a) {
             }
         } else if (!found) {
             // no exit face found: pull the photon towards the centroid and retry (:1932-1935, :2013-2024)
+#ifdef MMCB_COUNT_FIX           // analysis build: not-found events in the low 20 bits of kargs.trajcount, dropped photons above
+            atom_add_u32(a.trajcount, ((p.fixcount & 0xFF) < MMCB_MAX_TRIAL) ? 1u : (1u << 20));
+#endif
+
             if ((p.fixcount++ & 0xFF) < MMCB_MAX_TRIAL) {
                 float4 c = a.cent[p.eid - 1];
                 p.px += (c.x - p.px) * FIX_PHOTON;
                 p.py += (c.y - p.py) * FIX_PHOTON;
                 p.pz += (c.z - p.pz) * FIX_PHOTON;
             } else {
-                terminate = true;                           // r.eid = ID_UNDEFINED: dropped without detection
+                // The pulls did not help: the photon is not in this element.  It happens behind degenerate elements (the shipped sphshells mesh
+                // has one flat tetrahedron of 1e-15 mm^3 and 5 mm^2: its four plane distances are rounding noise, so the exit face -- and with
+                // it the neighbour -- is a coin toss, and the wrong neighbour does not contain the photon by 0.1 mm).  The reference gives such
+                // a photon up (r.eid = ID_UNDEFINED, :2027-2031); measured on config C2 that rule cost this engine 3.5e-4 of its photons, a
+                // deficit that grew to 0.5 % in the last time gate against BOTH reference programs (profiles/r2n_gate_drift.txt).  Instead the
+                // photon is relocated: it steps, without moving, through the face it is farthest beyond, until an element holds it -- at most
+                // MMCB_MAX_RELOC times in its life (a photon that cannot be placed is given up as before; an unbounded search can cycle
+                // between elements with minute steps of headway).  Leaving the mesh this way ends the photon.
+                const mmcb_tetrec* rr = a.tet + (p.eid - 1);
+                float worst = 0.f;
+                int nbw = 0;
+                #pragma unroll
+
+                for (int j = 0; j < 4; j++) {
+                    const float tn = __ldg(rr->d + j) - (p.px * __ldg(rr->nx + j) + p.py * __ldg(rr->ny + j) + p.pz * __ldg(rr->nz + j));
+
+                    if (tn < worst) {
+                        worst = tn;
+                        nbw = __ldg(rr->nb + j);
+                    }
+                }
+
+                const int nreloc = (p.fixcount >> 8) & 0xFF;
+
+                if (nbw > 0 && nreloc < MMCB_MAX_RELOC) {
+                    p.eid = nbw;
+                    p.fixcount = (p.fixcount & ~0xFFFF) | ((nreloc + 1) << 8);      // searches start over in the new element
+                } else {
+                    terminate = true;                       // r.eid = ID_UNDEFINED: dropped without detection
+                }
             }
         }
 

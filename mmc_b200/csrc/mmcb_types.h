@@ -4,8 +4,11 @@
 
 #define MMCB_MAX_DET      256       // point detectors kept in constant memory
 #define MMCB_MAX_SRCNUM   16        // patterns simulated together (photon sharing)
+#ifndef MMCB_MAX_TRIAL
 #define MMCB_MAX_TRIAL    3         // src/mmc_core.cl:355
+#endif
 #define MMCB_MAX_STALL    1000      // consecutive zero-length steps before a trapped photon is dropped
+#define MMCB_MAX_RELOC    16        // relocations of a photon that is not in its element (mmcb_kernel.cu, no-exit-face path) before it is given up
 #define MMCB_DEBUG_REC    6         // floats per trajectory record (src/mmc_core.cl:360)
 // Hot-line cache: the L2 serialises atomics that hit one 128-byte line (~0.7 G red/s measured, profiles/), and every
 // photon deposits next to the source.  The hottest lines of the accumulator volume (16 doubles / 32 floats worth of
