@@ -1294,9 +1294,10 @@ mmcb_photon_kernel(const mmcb_kargs a) {
 
             // progress guard (not in the reference): a photon that makes no headway for MMCB_MAX_STALL consecutive steps is
             // trapped between degenerate/inverted tetrahedra (the reference CPU path spins forever there) and is dropped
-            // fixcount: bits 0-7 = consecutive failed searches (the reference's `fixcount`, which it clears at every hop, :2010 -- also at a
-            // zero-length one), bits 8-15 = relocations of this photon (below; never cleared), bits 16+ = consecutive steps without headway
-            p.fixcount = (Lmove > 0.f) ? (p.fixcount & 0xFF00) : ((p.fixcount & ~0xFF) + 0x10000);
+            // fixcount: bits 0-7 = failed exit-face searches since the last step with headway (the reference's `fixcount`), bits 8-14 =
+            // relocations of this photon (below; never cleared), bit 15 = it has made headway at least once, bits 16+ = consecutive
+            // steps without headway
+            p.fixcount = (Lmove > 0.f) ? ((p.fixcount & 0x7F00) | 0x8000) : (p.fixcount + 0x10000);
 
             if (DET) {                                      // :1943-1945
                 if (type != acct) {
@@ -1408,11 +1409,14 @@ mmcb_photon_kernel(const mmcb_kargs a) {
                     }
                 }
 
-                const int nreloc = (p.fixcount >> 8) & 0xFF;
+                // Plain kernels only, and only photons that have moved: area sources and source slots (general kernels) launch photons
+                // outside their launch element, and the reference's results (adjoint Jacobians, tests/test_gpu_vs_reference_adjoint.py:
+                // +46 % with relocation) count on those being given up.
+                const int nreloc = (p.fixcount >> 8) & 0x7F;
 
-                if (nbw > 0 && nreloc < MMCB_MAX_RELOC) {
+                if (!GENERAL && nbw > 0 && nreloc < MMCB_MAX_RELOC && (p.fixcount & 0x8000)) {
                     p.eid = nbw;
-                    p.fixcount = (p.fixcount & ~0xFFFF) | ((nreloc + 1) << 8);      // searches start over in the new element
+                    p.fixcount = (p.fixcount & ~0x7FFF) | ((nreloc + 1) << 8);      // searches start over in the new element
                 } else {
                     terminate = true;                       // r.eid = ID_UNDEFINED: dropped without detection
                 }

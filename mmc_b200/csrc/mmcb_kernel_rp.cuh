@@ -493,7 +493,7 @@ mmcb_photon_kernel_rp(const mmcb_kargs a) {
                     p.px += Lmove * p.vx;                       // :1222
                     p.py += Lmove * p.vy;
                     p.pz += Lmove * p.vz;
-                    p.fixcount = (Lmove > 0.f) ? 0 : ((p.fixcount & ~0xFF) + 0x10000);      // progress guard + trial reset, see mmcb_photon_kernel
+                    p.fixcount = (Lmove > 0.f) ? 0 : (p.fixcount + 0x10000);      // progress guard, see mmcb_photon_kernel
 
                     if (DET) {                                  // :1943-1945
                         if (type != x.acct) {
