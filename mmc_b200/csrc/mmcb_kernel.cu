@@ -1411,7 +1411,7 @@ mmcb_photon_kernel(const mmcb_kargs a) {
 
                 // Plain kernels only, and only photons that have moved: area sources and source slots (general kernels) launch photons
                 // outside their launch element, and the reference's results (adjoint Jacobians, tests/test_gpu_vs_reference_adjoint.py:
-                // +46 % with relocation) count on those being given up.
+                // +46 % when a build relocated them and cleared the trial counter at zero-length steps) count on those being given up.
                 const int nreloc = (p.fixcount >> 8) & 0x7F;
 
                 if (!GENERAL && nbw > 0 && nreloc < MMCB_MAX_RELOC && (p.fixcount & 0x8000)) {
