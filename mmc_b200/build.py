@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmmc_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = ["mmcb_kernel.cu", "mmcb_post.cu", "mmcb_prep.cu", "mmcb_host.cu"]
-HEADERS = ["mmcb_types.h", os.path.join("..", "..", "include", "mmc_b200.h")]
+HEADERS = ["mmcb_types.h", "mmcb_kernel_rp.cuh", os.path.join("..", "..", "include", "mmc_b200.h")]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-use_fast_math", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--cudart", "static"]
 
